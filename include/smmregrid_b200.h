@@ -1,0 +1,184 @@
+/*
+ * smmregrid_b200.h -- C ABI of the B200-native weight-application operator.
+ *
+ * Drop-in boundary for the hot path of jhardenberg/smmregrid (v0.1.6).  The reference has
+ * no FFI; its seam is the opaque "weights matrix" object that every caller only builds,
+ * indexes per level and hands to tensordot.  Each entry point below cites the reference
+ * interface it replaces (paths relative to the reference root).  Plain C, no torch types;
+ * every function returns an int status (SMM_OK = 0) and never throws across the ABI.
+ * smm_last_error() returns a thread-local message for the last non-zero status.
+ *
+ * Ownership: a handle owns device copies of the operator (CSR, tile plan, dst_grid_imask,
+ * dst_grid_frac).  Arrays passed to create/set functions are HOST pointers, copied, never
+ * retained.  x / y of smm_apply* are DEVICE pointers owned by the caller (smm_apply_host
+ * takes HOST pointers and stages them itself).  A handle is immutable after creation
+ * except through smm_set_dst_mask / smm_mask_sum; smm_apply* are re-entrant across
+ * streams.  There is no CPU fallback: every function fails with SMM_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef SMMREGRID_B200_H
+#define SMMREGRID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMM_OK 0
+#define SMM_ERR_INVALID 1   /* bad argument (Python shim: ValueError)                     */
+#define SMM_ERR_RANGE 2     /* address outside [index_base, n + index_base) (ValueError)  */
+#define SMM_ERR_CUDA 3      /* CUDA runtime failure or no sm_100 device (RuntimeError)    */
+#define SMM_ERR_ALLOC 4     /* host or device allocation failure (MemoryError)            */
+#define SMM_ERR_DTYPE 5     /* unsupported dtype code (TypeError)                         */
+
+#define SMM_F32 0
+#define SMM_F64 1
+
+/* Which kernel family serves a level (smm_info.kernel). */
+#define SMM_KERNEL_STAGED 1 /* TMA-staged source footprint, register-resident weights     */
+#define SMM_KERNEL_GATHER 2 /* direct-gather CSR (scattered sources / oversized rows)     */
+
+typedef struct smm_handle smm_handle;
+typedef void *smm_stream_t; /* cudaStream_t; NULL = legacy default stream */
+
+typedef struct smm_info {
+    int64_t n_src, n_dst, nnz;   /* nnz after duplicate links were summed                 */
+    int32_t n_levels;            /* 1 for a 2-D operator                                  */
+    int32_t kernel;              /* SMM_KERNEL_* chosen for this level                    */
+    int32_t lanes_per_row;       /* staged plan: lanes sharing one destination row        */
+    int32_t links_per_lane;      /* staged plan: register-resident links per lane         */
+    int32_t rows_per_tile;       /* staged plan: destination rows per tile                */
+    int32_t n_tiles;
+    int32_t max_row_nnz;
+    int32_t max_tile_segments;
+    int64_t max_tile_elems;      /* largest staged source footprint of a tile (elements)  */
+    int64_t sum_tile_elems;      /* sum of staged footprints: source elements one batch   */
+                                 /* row pulls through TMA (>= touched columns)            */
+    int64_t touched_src;         /* distinct source columns with >= 1 link                */
+    int64_t device_bytes;        /* device memory held for this level                     */
+} smm_info;
+
+/*
+ * compute_weights_matrix (smmregrid/weights.py:25-44).
+ * Builds the device operator from CDO link arrays: src_address/dst_address are
+ * index_base-based (CDO: 1), remap_matrix is [nnz, num_wgts] row-major and only column 0
+ * is used (weights.py:33).  Duplicate (src,dst) links are summed like sparse.COO does.
+ */
+int smm_create(int64_t n_src, int64_t n_dst, int64_t nnz,
+               const int32_t *src_address, const int32_t *dst_address,
+               const double *remap_matrix, int32_t num_wgts, int32_t index_base,
+               int32_t device, smm_handle **out);
+
+/*
+ * compute_weights_matrix3d (smmregrid/weights.py:7-23) on the padded 3-D layout written by
+ * CdoGenerate.weightslist_to_3d (smmregrid/cdogenerate.py:310-343): arrays are
+ * [n_levels, nl_max] row-major (remap_matrix [n_levels, nl_max, num_wgts]); level i uses
+ * links [0, link_length[i]).
+ */
+int smm_create_levels(int32_t n_levels, const int64_t *link_length, int64_t nl_max,
+                      int64_t n_src, int64_t n_dst,
+                      const int32_t *src_address, const int32_t *dst_address,
+                      const double *remap_matrix, int32_t num_wgts, int32_t index_base,
+                      int32_t device, smm_handle **out);
+
+/* The reference drops the matrix object; here the handle is released explicitly. */
+int smm_destroy(smm_handle *h);
+
+int smm_get_info(const smm_handle *h, int32_t level, smm_info *out);
+
+/*
+ * mask_tensordot (smmregrid/weights.py:47-52) for one level (0 for 2-D):
+ *   t[dst] = sum_src src_imask[src] * W[src,dst] (float64, links in ascending-src order),
+ *   dst_imask[dst] = t < 0.5 ? 0 : 1.
+ * src_imask [n_src] and dst_imask_out [n_dst] are HOST int32 arrays.  The result is also
+ * installed as the level's dst_grid_imask, as mask_weights (weights.py:55-84) does.
+ * *any_masked_out (optional) = check_mask (weights.py:103-120): 1 if some dst cell is 0.
+ */
+int smm_mask_sum(smm_handle *h, int32_t level, const int32_t *src_imask,
+                 int32_t *dst_imask_out, int32_t *any_masked_out);
+
+/*
+ * Install the per-level epilogue vectors read by apply_weights (smmregrid/regrid.py:506-508):
+ * dst_grid_imask [n_dst] int32 (NULL keeps the current one) and dst_grid_frac [n_dst]
+ * float64 (NULL keeps the current one).  HOST pointers.
+ */
+int smm_set_dst_mask(smm_handle *h, int32_t level, const int32_t *dst_grid_imask,
+                     const double *dst_grid_frac);
+
+/*
+ * Numeric core of Regridder.apply_weights (smmregrid/regrid.py:536-570) on one level:
+ *   x [B, n_src] row-major with row stride ldx (elements), dtype x_dtype;
+ *   non-finite -> 1e20 (in x's dtype), Y = X.W accumulated in float64,
+ *   masked != 0:            Y[:, d] = NaN where dst_grid_imask[d] == 0     (:553-559)
+ *   remap_area_min > 0:     Y[:, d] = NaN where dst_grid_frac[d] < min     (:562-565)
+ *   Y > 1e19 -> NaN                                                         (:570)
+ *   y [B, n_dst] row stride ldy, dtype y_dtype (SMM_F64 = the reference's result_type;
+ *   SMM_F32 rounds the float64 result once at the store).
+ * x and y are DEVICE pointers; the launch is asynchronous on `stream`.
+ */
+int smm_apply(const smm_handle *h, int32_t level,
+              const void *x, int32_t x_dtype, int64_t B, int64_t ldx,
+              void *y, int32_t y_dtype, int64_t ldy,
+              int32_t masked, double remap_area_min, smm_stream_t stream);
+
+/*
+ * Regridder.regrid3d's level loop (smmregrid/regrid.py:387-410) as ONE grouped launch.
+ * For i in [0, n_sel): data level i uses weight level level_index[i] (the caller resolves
+ * the nearest-level rule of regrid.py:390-395).  Batch row b of data level i lives at
+ *   x + (b * x_batch_stride + i * x_level_stride) elements, and is written to
+ *   y + (b * y_batch_stride + i * y_level_stride) elements,
+ * which places every level directly at its final [.., L, n_dst] position (the concat +
+ * transpose of regrid.py:410-427).  masked[i] is the per-level flag of check_mask.
+ */
+int smm_apply_levels(const smm_handle *h, int32_t n_sel, const int32_t *level_index,
+                     const void *x, int32_t x_dtype, int64_t B,
+                     int64_t x_batch_stride, int64_t x_level_stride,
+                     void *y, int32_t y_dtype,
+                     int64_t y_batch_stride, int64_t y_level_stride,
+                     const uint8_t *masked, double remap_area_min, smm_stream_t stream);
+
+/*
+ * smm_apply for HOST buffers: x/y are host pointers (pinned or pageable); the batch axis
+ * is cut into chunks of `chunk_rows` (0 = auto) that are copied host->device, applied and
+ * copied back on alternating streams so copies overlap the kernel.  Synchronous: returns
+ * when y is complete.
+ */
+int smm_apply_host(const smm_handle *h, int32_t level,
+                   const void *x, int32_t x_dtype, int64_t B, int64_t ldx,
+                   void *y, int32_t y_dtype, int64_t ldy,
+                   int32_t masked, double remap_area_min, int64_t chunk_rows);
+
+
+/*
+ * Host-only introspection of the operator construction (no device needed): builds the
+ * same CSR + tile plan smm_create uploads, so the host logic can be verified on a CPU-only
+ * machine.  No compute entry point exists on the host side.
+ *   smm_host_plan_copy: any output pointer may be NULL.  Sizes: rowptr [n_dst+1], col/val
+ *   [nnz], tiles [n_tiles*8] int32 (row0,nrows,seg0,nseg,elems,pad*3), segs [n_segs*4]
+ *   uint32 (src,dst,len,pad), wplan/iplan [n_tiles*links_per_lane*256].
+ */
+typedef struct smm_host_plan smm_host_plan;
+int smm_host_plan_build(int64_t n_src, int64_t n_dst, int64_t nnz,
+                        const int32_t *src_address, const int32_t *dst_address,
+                        const double *remap_matrix, int32_t num_wgts, int32_t index_base,
+                        smm_host_plan **out);
+int smm_host_plan_info(const smm_host_plan *p, smm_info *out, int64_t *n_segs_out);
+int smm_host_plan_copy(const smm_host_plan *p, int32_t *rowptr, int32_t *col, double *val,
+                       int32_t *tiles, uint32_t *segs, double *wplan, uint16_t *iplan);
+void smm_host_plan_free(smm_host_plan *p);
+
+/* Force a kernel family for subsequent applies (testing/benchmark aid): 0 = automatic,
+ * SMM_KERNEL_STAGED (fails if the level has no staged plan) or SMM_KERNEL_GATHER. */
+int smm_set_kernel(smm_handle *h, int32_t kernel);
+
+/* Kernels launched by this library in the calling process so far (bench.py gpu_launches). */
+int64_t smm_launch_count(void);
+
+const char *smm_last_error(void);
+const char *smm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMMREGRID_B200_H */

@@ -1,0 +1,95 @@
+"""ctypes binding of the C ABI declared in ``include/smmregrid_b200.h``.
+
+The library must exist (``python -m smmregrid_b200._build`` or ``__graft_entry__.build()``);
+a missing library is a hard error -- this package has no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import _build
+
+SMM_OK, SMM_ERR_INVALID, SMM_ERR_RANGE, SMM_ERR_CUDA, SMM_ERR_ALLOC, SMM_ERR_DTYPE = range(6)
+SMM_F32, SMM_F64 = 0, 1
+SMM_KERNEL_STAGED, SMM_KERNEL_GATHER = 1, 2
+KERNEL_NAMES = {SMM_KERNEL_STAGED: "staged", SMM_KERNEL_GATHER: "gather"}
+
+i32, i64, f64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+vp = ctypes.c_void_p
+P = ctypes.POINTER
+
+
+class SmmInfo(ctypes.Structure):
+    _fields_ = [
+        ("n_src", i64), ("n_dst", i64), ("nnz", i64),
+        ("n_levels", i32), ("kernel", i32), ("lanes_per_row", i32), ("links_per_lane", i32),
+        ("rows_per_tile", i32), ("n_tiles", i32), ("max_row_nnz", i32), ("max_tile_segments", i32),
+        ("max_tile_elems", i64), ("sum_tile_elems", i64), ("touched_src", i64), ("device_bytes", i64),
+    ]
+
+    def asdict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["kernel_name"] = KERNEL_NAMES.get(self.kernel, "?")
+        return d
+
+
+# name -> (restype, argtypes): every symbol the header declares
+SIGNATURES = {
+    "smm_create": (ctypes.c_int, [i64, i64, i64, vp, vp, vp, i32, i32, i32, P(vp)]),
+    "smm_create_levels": (ctypes.c_int, [i32, vp, i64, i64, i64, vp, vp, vp, i32, i32, i32, P(vp)]),
+    "smm_destroy": (ctypes.c_int, [vp]),
+    "smm_get_info": (ctypes.c_int, [vp, i32, P(SmmInfo)]),
+    "smm_mask_sum": (ctypes.c_int, [vp, i32, vp, vp, P(i32)]),
+    "smm_set_dst_mask": (ctypes.c_int, [vp, i32, vp, vp]),
+    "smm_apply": (ctypes.c_int, [vp, i32, vp, i32, i64, i64, vp, i32, i64, i32, f64, vp]),
+    "smm_apply_levels": (ctypes.c_int, [vp, i32, vp, vp, i32, i64, i64, i64, vp, i32, i64, i64, vp, f64, vp]),
+    "smm_apply_host": (ctypes.c_int, [vp, i32, vp, i32, i64, i64, vp, i32, i64, i32, f64, i64]),
+    "smm_host_plan_build": (ctypes.c_int, [i64, i64, i64, vp, vp, vp, i32, i32, P(vp)]),
+    "smm_host_plan_info": (ctypes.c_int, [vp, P(SmmInfo), P(i64)]),
+    "smm_host_plan_copy": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
+    "smm_host_plan_free": (None, [vp]),
+    "smm_set_kernel": (ctypes.c_int, [vp, i32]),
+    "smm_launch_count": (i64, []),
+    "smm_last_error": (ctypes.c_char_p, []),
+    "smm_version": (ctypes.c_char_p, []),
+}
+
+_lib = None
+
+
+class SmmError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load the shared library (never builds silently, never falls back)."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise SmmError(
+                f"{path} is missing: build it with `python -m smmregrid_b200._build` "
+                "(nvcc, sm_100a). smmregrid_b200 has no CPU fallback.")
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+_EXC = {SMM_ERR_INVALID: ValueError, SMM_ERR_RANGE: ValueError, SMM_ERR_CUDA: SmmError,
+        SMM_ERR_ALLOC: MemoryError, SMM_ERR_DTYPE: TypeError}
+
+
+def check(rc: int):
+    """Map a status code to the exception type the reference would raise."""
+    if rc != SMM_OK:
+        msg = load().smm_last_error().decode("utf-8", "replace")
+        raise _EXC.get(rc, SmmError)(msg)

@@ -1,0 +1,681 @@
+// smm_api.cu -- C ABI (include/smmregrid_b200.h) over the sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/smmregrid_b200.h"
+#include "smm_kernels.cuh"
+#include "smm_plan.h"
+
+using namespace smm;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(e__ == cudaErrorMemoryAllocation ? SMM_ERR_ALLOC : SMM_ERR_CUDA,   \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+    } while (0)
+
+struct LevelDev {
+    int64_t n_src = 0, n_dst = 0, nnz = 0, touched = 0;
+    int32_t max_row_nnz = 0;
+    int32_t *rowptr = nullptr, *col = nullptr;
+    double *val = nullptr;
+    bool staged = false;
+    std::string why_not_staged;
+    int32_t lpr = 0, kpl = 0, rpt = 0, ntiles = 0, max_segs = 0;
+    int64_t max_elems = 0, sum_elems = 0;
+    TileDesc *tiles = nullptr;
+    Seg *segs = nullptr;
+    double *wplan = nullptr;
+    uint16_t *iplan = nullptr;
+    int32_t *imask = nullptr;
+    double *frac = nullptr;
+    bool has_imask = false, has_frac = false;
+    int64_t device_bytes = 0;
+};
+
+struct HostSlot {
+    void *dx = nullptr, *dy = nullptr;
+    size_t cap_x = 0, cap_y = 0;
+    cudaStream_t stream = nullptr;
+};
+
+}  // namespace
+
+struct smm_handle {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    int force_kernel = 0;
+    std::vector<LevelDev> levels;
+    std::mutex host_mu;
+    HostSlot slots[3];
+};
+
+namespace {
+
+template <typename T>
+int upload(T **dptr, const std::vector<T> &v, int64_t &bytes)
+{
+    *dptr = nullptr;
+    const size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(dptr), n));
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    bytes += static_cast<int64_t>(n);
+    return SMM_OK;
+}
+
+void free_level(LevelDev &L)
+{
+    cudaFree(L.rowptr); cudaFree(L.col); cudaFree(L.val);
+    cudaFree(L.tiles); cudaFree(L.segs); cudaFree(L.wplan); cudaFree(L.iplan);
+    cudaFree(L.imask); cudaFree(L.frac);
+    L = LevelDev{};
+}
+
+int upload_level(const HostCsr &csr, const HostPlan &plan, LevelDev &L)
+{
+    L.n_src = csr.n_src; L.n_dst = csr.n_dst; L.nnz = static_cast<int64_t>(csr.col.size());
+    L.touched = csr.touched_src; L.max_row_nnz = csr.max_row_nnz;
+    int rc;
+    if ((rc = upload(&L.rowptr, csr.rowptr, L.device_bytes))) return rc;
+    if ((rc = upload(&L.col, csr.col, L.device_bytes))) return rc;
+    if ((rc = upload(&L.val, csr.val, L.device_bytes))) return rc;
+    L.staged = plan.ok;
+    L.why_not_staged = plan.why;
+    L.lpr = plan.lpr; L.kpl = plan.kpl; L.rpt = plan.rows_per_tile;
+    if (plan.ok) {
+        L.ntiles = static_cast<int32_t>(plan.tiles.size());
+        L.max_segs = plan.max_tile_segments;
+        L.max_elems = plan.max_tile_elems;
+        L.sum_elems = plan.sum_tile_elems;
+        if ((rc = upload(&L.tiles, plan.tiles, L.device_bytes))) return rc;
+        if ((rc = upload(&L.segs, plan.segs, L.device_bytes))) return rc;
+        if ((rc = upload(&L.wplan, plan.wplan, L.device_bytes))) return rc;
+        if ((rc = upload(&L.iplan, plan.iplan, L.device_bytes))) return rc;
+    }
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&L.imask), static_cast<size_t>(L.n_dst) * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&L.frac), static_cast<size_t>(L.n_dst) * sizeof(double)));
+    L.device_bytes += L.n_dst * 12;
+    return SMM_OK;
+}
+
+int open_device(int device, smm_handle *h)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SMM_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                      " (smmregrid_b200 has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(SMM_ERR_INVALID, "device index out of range");
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    if (p.major != 10)
+        return fail(SMM_ERR_CUDA, "smmregrid_b200 kernels are built for sm_100a only; device is sm_" +
+                                      std::to_string(p.major) + std::to_string(p.minor));
+    CUDA_TRY(cudaSetDevice(device));
+    h->device = device;
+    h->sm_count = p.multiProcessorCount;
+    h->smem_optin = p.sharedMemPerBlockOptin;
+    return SMM_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------ launch dispatch
+
+template <typename TX, typename TY>
+int launch_staged_t(int lpr, int kpl, dim3 grid, size_t smem, cudaStream_t st, const JobBatch &jb,
+                    const ApplyArgs &a)
+{
+#define SMM_CASE(L_, K_)                                                                          \
+    if (lpr == L_ && kpl == K_) {                                                                 \
+        auto kfn = staged_kernel<TX, TY, L_, K_>;                                                 \
+        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                      static_cast<int>(smem)));                                   \
+        kfn<<<grid, kStagedThreads, smem, st>>>(jb, a);                                           \
+        CUDA_TRY(cudaGetLastError());                                                             \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                       \
+        return SMM_OK;                                                                            \
+    }
+    SMM_CASE(1, 4) SMM_CASE(2, 4) SMM_CASE(1, 16) SMM_CASE(2, 16) SMM_CASE(4, 16) SMM_CASE(8, 16)
+    SMM_CASE(16, 16) SMM_CASE(32, 16)
+#undef SMM_CASE
+    return fail(SMM_ERR_INVALID, "no staged kernel for this lane configuration");
+}
+
+template <typename TX, typename TY>
+int launch_gather_t(int lpr, dim3 grid, cudaStream_t st, const JobBatch &jb, const ApplyArgs &a)
+{
+    if (lpr == 1) gather_kernel<TX, TY, 1><<<grid, kGatherThreads, 0, st>>>(jb, a);
+    else if (lpr == 4) gather_kernel<TX, TY, 4><<<grid, kGatherThreads, 0, st>>>(jb, a);
+    else gather_kernel<TX, TY, 32><<<grid, kGatherThreads, 0, st>>>(jb, a);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return SMM_OK;
+}
+
+#define SMM_DTYPE_DISPATCH(FN, ...)                                                    \
+    ((x_dtype == SMM_F32 && y_dtype == SMM_F32)   ? FN<float, float>(__VA_ARGS__)      \
+     : (x_dtype == SMM_F32 && y_dtype == SMM_F64) ? FN<float, double>(__VA_ARGS__)     \
+     : (x_dtype == SMM_F64 && y_dtype == SMM_F32) ? FN<double, float>(__VA_ARGS__)     \
+                                                  : FN<double, double>(__VA_ARGS__))
+
+struct JobSpec {
+    int32_t level;
+    const void *x;
+    void *y;
+    int32_t masked;
+};
+
+int64_t pick_chunks(int64_t B, int64_t blocks_total, int sm_count, int64_t multiple, int64_t &chunk)
+{
+    // ~16 waves of 2 CTAs/SM so the tail is a few percent, but at least 32 batch rows per
+    // work item so the per-item link load stays amortised.
+    const int64_t target = static_cast<int64_t>(sm_count) * 2 * 16;
+    int64_t nchunks = (target + blocks_total - 1) / std::max<int64_t>(blocks_total, 1);
+    const int64_t max_chunks = std::max<int64_t>(1, B / 32);
+    nchunks = std::max<int64_t>(1, std::min(nchunks, max_chunks));
+    chunk = (B + nchunks - 1) / nchunks;
+    chunk = (chunk + multiple - 1) / multiple * multiple;
+    return (B + chunk - 1) / chunk;
+}
+
+int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t x_dtype,
+                int32_t y_dtype, int64_t B, int64_t xbs, int64_t ybs, double area_min,
+                cudaStream_t st)
+{
+    if (B == 0 || specs.empty()) return SMM_OK;
+    const size_t sx = x_dtype == SMM_F32 ? 4 : 8;
+    std::vector<JobSpec> staged, gather;
+    for (const JobSpec &s : specs) {
+        const LevelDev &L = h->levels[s.level];
+        if (s.masked && !L.has_imask)
+            return fail(SMM_ERR_INVALID, "masked apply but dst_grid_imask was never set for level " +
+                                             std::to_string(s.level));
+        if (area_min > 0.0 && !L.has_frac)
+            return fail(SMM_ERR_INVALID, "remap_area_min > 0 but dst_grid_frac was never set for level " +
+                                             std::to_string(s.level));
+        bool ok = L.staged && h->force_kernel != SMM_KERNEL_GATHER;
+        // TMA bulk copies need 16-byte aligned rows and lengths
+        ok = ok && (reinterpret_cast<uintptr_t>(s.x) % 16 == 0) && ((xbs * sx) % 16 == 0) &&
+             ((L.n_src * sx) % 16 == 0);
+        // at least two stages must fit
+        ok = ok && (kSmemHeader + round_up(static_cast<size_t>(L.max_segs) * sizeof(Seg), 128) +
+                        2 * round_up(static_cast<size_t>(L.max_elems) * sx, 128) <= h->smem_optin);
+        if (!ok && h->force_kernel == SMM_KERNEL_STAGED)
+            return fail(SMM_ERR_INVALID, "staged kernel forced but unavailable for level " +
+                                             std::to_string(s.level) + ": " +
+                                             (L.staged ? std::string("slab alignment / footprint size")
+                                                       : L.why_not_staged));
+        (ok ? staged : gather).push_back(s);
+    }
+
+    ApplyArgs a{};
+    a.B = B; a.x_bstride = xbs; a.y_bstride = ybs; a.remap_area_min = area_min;
+
+    auto fill_job = [&](const JobSpec &s, LevelJob &j) {
+        const LevelDev &L = h->levels[s.level];
+        j.tiles = L.tiles; j.segs = L.segs; j.wplan = L.wplan; j.iplan = L.iplan;
+        j.rowptr = L.rowptr; j.col = L.col; j.val = L.val;
+        j.imask = L.imask; j.frac = L.frac;
+        j.x = s.x; j.y = s.y; j.masked = s.masked; j.pad = 0;
+    };
+
+    // ---- staged launches, kMaxJobs levels at a time
+    for (size_t g0 = 0; g0 < staged.size(); g0 += kMaxJobs) {
+        const size_t g1 = std::min(staged.size(), g0 + kMaxJobs);
+        JobBatch jb{};
+        int64_t tiles_total = 0;
+        size_t max_segs = 0, max_elems = 0;
+        int lpr = 0, kpl = 0;
+        for (size_t g = g0; g < g1; ++g) {
+            const LevelDev &L = h->levels[staged[g].level];
+            tiles_total += L.ntiles;
+            max_segs = std::max<size_t>(max_segs, L.max_segs);
+            max_elems = std::max<size_t>(max_elems, L.max_elems);
+            lpr = L.lpr; kpl = L.kpl;
+            a.n_src = L.n_src; a.n_dst = L.n_dst;
+        }
+        int64_t chunk = 0;
+        const int64_t nchunks = pick_chunks(B, tiles_total, h->sm_count, 1, chunk);
+        a.chunk = chunk; a.nchunks = static_cast<int32_t>(nchunks);
+        const size_t stage_off = kSmemHeader + round_up(max_segs * sizeof(Seg), 128);
+        const size_t stage_bytes = std::max<size_t>(128, round_up(max_elems * sx, 128));
+        const size_t half = (228u * 1024u - 2u * 1024u) / 2u - 1024u;   // two CTAs per SM
+        size_t S = half > stage_off ? (half - stage_off) / stage_bytes : 0;
+        if (S < 3) S = (h->smem_optin - stage_off) / stage_bytes;        // one CTA per SM
+        S = std::min<size_t>(S, kMaxStages);
+        if (S < 2) return fail(SMM_ERR_INVALID, "internal: staged footprint does not fit");
+        a.nstages = static_cast<int32_t>(S);
+        a.stage_bytes = static_cast<uint32_t>(stage_bytes);
+        a.stage_off = static_cast<uint32_t>(stage_off);
+        const size_t smem = stage_off + S * stage_bytes;
+        int64_t item = 0;
+        jb.njobs = static_cast<int32_t>(g1 - g0);
+        for (size_t g = g0; g < g1; ++g) {
+            LevelJob &j = jb.jobs[g - g0];
+            fill_job(staged[g], j);
+            j.nblocks = h->levels[staged[g].level].ntiles;
+            j.item0 = static_cast<int32_t>(item);
+            item += static_cast<int64_t>(j.nblocks) * nchunks;
+        }
+        if (item > INT32_MAX) return fail(SMM_ERR_INVALID, "too many work items in one launch");
+        if (item == 0) continue;
+        const dim3 grid(static_cast<unsigned>(item));
+        const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, lpr, kpl, grid, smem, st, jb, a);
+        if (rc) return rc;
+    }
+
+    // ---- gather launches
+    for (size_t g0 = 0; g0 < gather.size(); g0 += kMaxJobs) {
+        const size_t g1 = std::min(gather.size(), g0 + kMaxJobs);
+        JobBatch jb{};
+        int64_t nnz = 0, rows = 0;
+        for (size_t g = g0; g < g1; ++g) {
+            const LevelDev &L = h->levels[gather[g].level];
+            nnz += L.nnz; rows += L.n_dst;
+            a.n_src = L.n_src; a.n_dst = L.n_dst;
+        }
+        const double avg = rows ? static_cast<double>(nnz) / rows : 0.0;
+        const int lpr = avg <= 2.0 ? 1 : (avg <= 24.0 ? 4 : 32);
+        const int rpb = kGatherThreads / lpr;
+        int64_t blocks_total = 0;
+        for (size_t g = g0; g < g1; ++g)
+            blocks_total += (h->levels[gather[g].level].n_dst + rpb - 1) / rpb;
+        int64_t chunk = 0;
+        const int64_t nchunks = pick_chunks(B, blocks_total, h->sm_count, kGatherBT, chunk);
+        a.chunk = chunk; a.nchunks = static_cast<int32_t>(nchunks);
+        a.nstages = 0; a.stage_bytes = 0; a.stage_off = 0;
+        int64_t item = 0;
+        jb.njobs = static_cast<int32_t>(g1 - g0);
+        for (size_t g = g0; g < g1; ++g) {
+            LevelJob &j = jb.jobs[g - g0];
+            fill_job(gather[g], j);
+            j.nblocks = static_cast<int32_t>((h->levels[gather[g].level].n_dst + rpb - 1) / rpb);
+            j.item0 = static_cast<int32_t>(item);
+            item += static_cast<int64_t>(j.nblocks) * nchunks;
+        }
+        if (item > INT32_MAX) return fail(SMM_ERR_INVALID, "too many work items in one launch");
+        const dim3 grid(static_cast<unsigned>(item));
+        const int rc = SMM_DTYPE_DISPATCH(launch_gather_t, lpr, grid, st, jb, a);
+        if (rc) return rc;
+    }
+    return SMM_OK;
+}
+
+int check_dtypes(int32_t x_dtype, int32_t y_dtype)
+{
+    if ((x_dtype != SMM_F32 && x_dtype != SMM_F64) || (y_dtype != SMM_F32 && y_dtype != SMM_F64))
+        return fail(SMM_ERR_DTYPE, "dtype must be SMM_F32 (0) or SMM_F64 (1)");
+    return SMM_OK;
+}
+
+int check_level(const smm_handle *h, int32_t level)
+{
+    if (!h) return fail(SMM_ERR_INVALID, "null handle");
+    if (level < 0 || level >= static_cast<int32_t>(h->levels.size()))
+        return fail(SMM_ERR_INVALID, "level " + std::to_string(level) + " out of range [0, " +
+                                         std::to_string(h->levels.size()) + ")");
+    return SMM_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+
+extern "C" {
+
+int smm_create(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t *src_address,
+               const int32_t *dst_address, const double *remap_matrix, int32_t num_wgts,
+               int32_t index_base, int32_t device, smm_handle **out)
+{
+    const int64_t ll = nnz;
+    return smm_create_levels(1, &ll, nnz, n_src, n_dst, src_address, dst_address, remap_matrix,
+                             num_wgts, index_base, device, out);
+}
+
+int smm_create_levels(int32_t n_levels, const int64_t *link_length, int64_t nl_max, int64_t n_src,
+                      int64_t n_dst, const int32_t *src_address, const int32_t *dst_address,
+                      const double *remap_matrix, int32_t num_wgts, int32_t index_base,
+                      int32_t device, smm_handle **out)
+{
+    if (!out) return fail(SMM_ERR_INVALID, "null output handle pointer");
+    *out = nullptr;
+    if (n_levels < 1 || !link_length || nl_max < 0)
+        return fail(SMM_ERR_INVALID, "smm_create_levels: n_levels >= 1, link_length and nl_max >= 0 required");
+    for (int32_t i = 0; i < n_levels; ++i)
+        if (link_length[i] < 0 || link_length[i] > nl_max)
+            return fail(SMM_ERR_INVALID, "link_length[" + std::to_string(i) + "] outside [0, nl_max]");
+
+    smm_handle *h = new (std::nothrow) smm_handle();
+    if (!h) return fail(SMM_ERR_ALLOC, "host allocation failed");
+    int rc = open_device(device, h);
+    if (rc) { delete h; return rc; }
+
+    std::vector<HostCsr> csrs(static_cast<size_t>(n_levels));
+    std::string err;
+    int32_t max_row = 0;
+    for (int32_t i = 0; i < n_levels; ++i) {
+        const int64_t o = static_cast<int64_t>(i) * nl_max;
+        rc = build_csr(n_src, n_dst, link_length[i], src_address ? src_address + o : nullptr,
+                       dst_address ? dst_address + o : nullptr,
+                       remap_matrix ? remap_matrix + o * num_wgts : nullptr, num_wgts, index_base,
+                       csrs[i], err);
+        if (rc) { delete h; return fail(rc, (n_levels > 1 ? "level " + std::to_string(i) + ": " : "") + err); }
+        max_row = std::max(max_row, csrs[i].max_row_nnz);
+    }
+    // one lane configuration for every level so a grouped launch runs a single kernel
+    int32_t lpr = 0, kpl = 0;
+    const bool cfg = choose_lanes(max_row, lpr, kpl);
+    h->levels.resize(static_cast<size_t>(n_levels));
+    for (int32_t i = 0; i < n_levels; ++i) {
+        HostPlan plan;
+        if (cfg) build_plan(csrs[i], lpr, kpl, plan);
+        else plan.why = "a destination row has more than 512 links";
+        rc = upload_level(csrs[i], plan, h->levels[i]);
+        if (rc) { smm_destroy(h); return rc; }
+        csrs[i] = HostCsr{};
+    }
+    *out = h;
+    return SMM_OK;
+}
+
+int smm_destroy(smm_handle *h)
+{
+    if (!h) return SMM_OK;
+    {
+        DeviceGuard g(h->device);
+        for (LevelDev &L : h->levels) free_level(L);
+        for (HostSlot &s : h->slots) {
+            cudaFree(s.dx); cudaFree(s.dy);
+            if (s.stream) cudaStreamDestroy(s.stream);
+        }
+    }
+    delete h;
+    return SMM_OK;
+}
+
+int smm_get_info(const smm_handle *h, int32_t level, smm_info *out)
+{
+    int rc = check_level(h, level);
+    if (rc) return rc;
+    if (!out) return fail(SMM_ERR_INVALID, "null smm_info");
+    const LevelDev &L = h->levels[level];
+    std::memset(out, 0, sizeof(*out));
+    out->n_src = L.n_src; out->n_dst = L.n_dst; out->nnz = L.nnz;
+    out->n_levels = static_cast<int32_t>(h->levels.size());
+    const bool use_staged = L.staged && h->force_kernel != SMM_KERNEL_GATHER;
+    out->kernel = use_staged ? SMM_KERNEL_STAGED : SMM_KERNEL_GATHER;
+    out->lanes_per_row = L.lpr; out->links_per_lane = L.kpl; out->rows_per_tile = L.rpt;
+    out->n_tiles = L.ntiles; out->max_row_nnz = L.max_row_nnz;
+    out->max_tile_segments = L.max_segs; out->max_tile_elems = L.max_elems;
+    out->sum_tile_elems = L.sum_elems; out->touched_src = L.touched;
+    out->device_bytes = L.device_bytes;
+    return SMM_OK;
+}
+
+int smm_mask_sum(smm_handle *h, int32_t level, const int32_t *src_imask, int32_t *dst_imask_out,
+                 int32_t *any_masked_out)
+{
+    int rc = check_level(h, level);
+    if (rc) return rc;
+    if (!src_imask) return fail(SMM_ERR_INVALID, "null src_imask");
+    DeviceGuard g(h->device);
+    LevelDev &L = h->levels[level];
+    int32_t *d_src = nullptr, *d_flag = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_src), static_cast<size_t>(L.n_src) * sizeof(int32_t)));
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_flag), sizeof(int32_t));
+    if (e != cudaSuccess) { cudaFree(d_src); return fail(SMM_ERR_ALLOC, cudaGetErrorString(e)); }
+    e = cudaMemcpy(d_src, src_imask, static_cast<size_t>(L.n_src) * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_flag, 0, sizeof(int32_t));
+    if (e == cudaSuccess) {
+        const int threads = 256;
+        const unsigned blocks = static_cast<unsigned>((L.n_dst + threads - 1) / threads);
+        mask_sum_kernel<<<blocks, threads>>>(L.rowptr, L.col, L.val, d_src, L.imask, d_flag, L.n_dst);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        e = cudaGetLastError();
+    }
+    int32_t flag = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&flag, d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && dst_imask_out)
+        e = cudaMemcpy(dst_imask_out, L.imask, static_cast<size_t>(L.n_dst) * sizeof(int32_t),
+                       cudaMemcpyDeviceToHost);
+    cudaFree(d_src); cudaFree(d_flag);
+    if (e != cudaSuccess) return fail(SMM_ERR_CUDA, std::string("smm_mask_sum: ") + cudaGetErrorString(e));
+    L.has_imask = true;
+    if (any_masked_out) *any_masked_out = flag;
+    return SMM_OK;
+}
+
+int smm_set_dst_mask(smm_handle *h, int32_t level, const int32_t *dst_grid_imask, const double *dst_grid_frac)
+{
+    int rc = check_level(h, level);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    LevelDev &L = h->levels[level];
+    if (dst_grid_imask) {
+        CUDA_TRY(cudaMemcpy(L.imask, dst_grid_imask, static_cast<size_t>(L.n_dst) * sizeof(int32_t),
+                            cudaMemcpyHostToDevice));
+        L.has_imask = true;
+    }
+    if (dst_grid_frac) {
+        CUDA_TRY(cudaMemcpy(L.frac, dst_grid_frac, static_cast<size_t>(L.n_dst) * sizeof(double),
+                            cudaMemcpyHostToDevice));
+        L.has_frac = true;
+    }
+    return SMM_OK;
+}
+
+int smm_apply(const smm_handle *h, int32_t level, const void *x, int32_t x_dtype, int64_t B,
+              int64_t ldx, void *y, int32_t y_dtype, int64_t ldy, int32_t masked,
+              double remap_area_min, smm_stream_t stream)
+{
+    int rc = check_level(h, level);
+    if (rc) return rc;
+    if ((rc = check_dtypes(x_dtype, y_dtype))) return rc;
+    if (B < 0) return fail(SMM_ERR_INVALID, "B must be >= 0");
+    if (B == 0) return SMM_OK;
+    const LevelDev &L = h->levels[level];
+    if (!x || !y) return fail(SMM_ERR_INVALID, "null x or y");
+    if (ldx < L.n_src || ldy < L.n_dst) return fail(SMM_ERR_INVALID, "ldx < n_src or ldy < n_dst");
+    if (!(remap_area_min >= 0.0 && remap_area_min <= 1.0))
+        return fail(SMM_ERR_INVALID, "The remap_area_min provided must be between 0.0 and 1.0");
+    DeviceGuard g(h->device);
+    std::vector<JobSpec> specs{JobSpec{level, x, y, masked ? 1 : 0}};
+    return launch_jobs(h, specs, x_dtype, y_dtype, B, ldx, ldy, remap_area_min,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int smm_apply_levels(const smm_handle *h, int32_t n_sel, const int32_t *level_index, const void *x,
+                     int32_t x_dtype, int64_t B, int64_t x_batch_stride, int64_t x_level_stride,
+                     void *y, int32_t y_dtype, int64_t y_batch_stride, int64_t y_level_stride,
+                     const uint8_t *masked, double remap_area_min, smm_stream_t stream)
+{
+    if (!h) return fail(SMM_ERR_INVALID, "null handle");
+    int rc;
+    if ((rc = check_dtypes(x_dtype, y_dtype))) return rc;
+    if (n_sel < 0 || B < 0) return fail(SMM_ERR_INVALID, "n_sel and B must be >= 0");
+    if (n_sel == 0 || B == 0) return SMM_OK;
+    if (!level_index || !x || !y) return fail(SMM_ERR_INVALID, "null level_index, x or y");
+    if (!(remap_area_min >= 0.0 && remap_area_min <= 1.0))
+        return fail(SMM_ERR_INVALID, "The remap_area_min provided must be between 0.0 and 1.0");
+    const size_t sx = x_dtype == SMM_F32 ? 4 : 8, sy = y_dtype == SMM_F32 ? 4 : 8;
+    std::vector<JobSpec> specs;
+    specs.reserve(static_cast<size_t>(n_sel));
+    for (int32_t i = 0; i < n_sel; ++i) {
+        if ((rc = check_level(h, level_index[i]))) return rc;
+        JobSpec s;
+        s.level = level_index[i];
+        s.x = static_cast<const char *>(x) + static_cast<int64_t>(i) * x_level_stride * static_cast<int64_t>(sx);
+        s.y = static_cast<char *>(y) + static_cast<int64_t>(i) * y_level_stride * static_cast<int64_t>(sy);
+        s.masked = masked ? (masked[i] ? 1 : 0) : 0;
+        specs.push_back(s);
+    }
+    DeviceGuard g(h->device);
+    return launch_jobs(h, specs, x_dtype, y_dtype, B, x_batch_stride, y_batch_stride, remap_area_min,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int smm_apply_host(const smm_handle *hc, int32_t level, const void *x, int32_t x_dtype, int64_t B,
+                   int64_t ldx, void *y, int32_t y_dtype, int64_t ldy, int32_t masked,
+                   double remap_area_min, int64_t chunk_rows)
+{
+    int rc = check_level(hc, level);
+    if (rc) return rc;
+    if ((rc = check_dtypes(x_dtype, y_dtype))) return rc;
+    if (B < 0) return fail(SMM_ERR_INVALID, "B must be >= 0");
+    if (B == 0) return SMM_OK;
+    if (!x || !y) return fail(SMM_ERR_INVALID, "null x or y");
+    smm_handle *h = const_cast<smm_handle *>(hc);
+    const LevelDev &L = h->levels[level];
+    if (ldx < L.n_src || ldy < L.n_dst) return fail(SMM_ERR_INVALID, "ldx < n_src or ldy < n_dst");
+    const size_t sx = x_dtype == SMM_F32 ? 4 : 8, sy = y_dtype == SMM_F32 ? 4 : 8;
+    if (chunk_rows <= 0) {
+        // ~256 MB of source per chunk, at least 32 rows when the batch allows
+        chunk_rows = std::max<int64_t>(32, (int64_t{256} << 20) / std::max<int64_t>(1, L.n_src * sx));
+    }
+    chunk_rows = std::min(chunk_rows, B);
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    DeviceGuard g(h->device);
+    const size_t need_x = static_cast<size_t>(chunk_rows) * L.n_src * sx;
+    const size_t need_y = static_cast<size_t>(chunk_rows) * L.n_dst * sy;
+    const int nslots = B > chunk_rows ? 3 : 1;
+    for (int s = 0; s < nslots; ++s) {
+        HostSlot &sl = h->slots[s];
+        if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (sl.cap_x < need_x) {
+            cudaFree(sl.dx); sl.dx = nullptr; sl.cap_x = 0;
+            CUDA_TRY(cudaMalloc(&sl.dx, need_x));
+            sl.cap_x = need_x;
+        }
+        if (sl.cap_y < need_y) {
+            cudaFree(sl.dy); sl.dy = nullptr; sl.cap_y = 0;
+            CUDA_TRY(cudaMalloc(&sl.dy, need_y));
+            sl.cap_y = need_y;
+        }
+    }
+    int slot = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk_rows, slot = (slot + 1) % nslots) {
+        const int64_t nb = std::min(chunk_rows, B - b0);
+        HostSlot &sl = h->slots[slot];
+        // stream order serialises reuse of this slot's buffers with its previous chunk
+        const char *xs = static_cast<const char *>(x) + b0 * ldx * static_cast<int64_t>(sx);
+        char *ys = static_cast<char *>(y) + b0 * ldy * static_cast<int64_t>(sy);
+        CUDA_TRY(cudaMemcpy2DAsync(sl.dx, L.n_src * sx, xs, ldx * sx, L.n_src * sx, nb,
+                                   cudaMemcpyHostToDevice, sl.stream));
+        std::vector<JobSpec> specs{JobSpec{level, sl.dx, sl.dy, masked ? 1 : 0}};
+        rc = launch_jobs(h, specs, x_dtype, y_dtype, nb, L.n_src, L.n_dst, remap_area_min, sl.stream);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpy2DAsync(ys, ldy * sy, sl.dy, L.n_dst * sy, L.n_dst * sy, nb,
+                                   cudaMemcpyDeviceToHost, sl.stream));
+    }
+    for (int s = 0; s < nslots; ++s) CUDA_TRY(cudaStreamSynchronize(h->slots[s].stream));
+    return SMM_OK;
+}
+
+// ---- host-only introspection (no device): CSR + plan exactly as smm_create builds them
+
+struct smm_host_plan {
+    HostCsr csr;
+    HostPlan plan;
+};
+
+int smm_host_plan_build(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t *src_address,
+                        const int32_t *dst_address, const double *remap_matrix, int32_t num_wgts,
+                        int32_t index_base, smm_host_plan **out)
+{
+    if (!out) return fail(SMM_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    smm_host_plan *p = new (std::nothrow) smm_host_plan();
+    if (!p) return fail(SMM_ERR_ALLOC, "host allocation failed");
+    std::string err;
+    int rc = build_csr(n_src, n_dst, nnz, src_address, dst_address, remap_matrix, num_wgts,
+                       index_base, p->csr, err);
+    if (rc) { delete p; return fail(rc, err); }
+    build_plan(p->csr, 0, 0, p->plan);
+    *out = p;
+    return SMM_OK;
+}
+
+int smm_host_plan_info(const smm_host_plan *p, smm_info *out, int64_t *n_segs_out)
+{
+    if (!p || !out) return fail(SMM_ERR_INVALID, "null argument");
+    std::memset(out, 0, sizeof(*out));
+    out->n_src = p->csr.n_src; out->n_dst = p->csr.n_dst;
+    out->nnz = static_cast<int64_t>(p->csr.col.size());
+    out->n_levels = 1;
+    out->kernel = p->plan.ok ? SMM_KERNEL_STAGED : SMM_KERNEL_GATHER;
+    out->lanes_per_row = p->plan.lpr; out->links_per_lane = p->plan.kpl;
+    out->rows_per_tile = p->plan.rows_per_tile;
+    out->n_tiles = p->plan.ok ? static_cast<int32_t>(p->plan.tiles.size()) : 0;
+    out->max_row_nnz = p->csr.max_row_nnz;
+    out->max_tile_segments = p->plan.max_tile_segments;
+    out->max_tile_elems = p->plan.max_tile_elems;
+    out->sum_tile_elems = p->plan.sum_tile_elems;
+    out->touched_src = p->csr.touched_src;
+    if (n_segs_out) *n_segs_out = p->plan.ok ? static_cast<int64_t>(p->plan.segs.size()) : 0;
+    return SMM_OK;
+}
+
+int smm_host_plan_copy(const smm_host_plan *p, int32_t *rowptr, int32_t *col, double *val,
+                       int32_t *tiles, uint32_t *segs, double *wplan, uint16_t *iplan)
+{
+    if (!p) return fail(SMM_ERR_INVALID, "null plan");
+    auto cp = [](void *dst, const void *src, size_t n) { if (dst && n) std::memcpy(dst, src, n); };
+    cp(rowptr, p->csr.rowptr.data(), p->csr.rowptr.size() * sizeof(int32_t));
+    cp(col, p->csr.col.data(), p->csr.col.size() * sizeof(int32_t));
+    cp(val, p->csr.val.data(), p->csr.val.size() * sizeof(double));
+    if (p->plan.ok) {
+        static_assert(sizeof(TileDesc) == 32 && sizeof(Seg) == 16, "layout is part of the ABI");
+        cp(tiles, p->plan.tiles.data(), p->plan.tiles.size() * sizeof(TileDesc));
+        cp(segs, p->plan.segs.data(), p->plan.segs.size() * sizeof(Seg));
+        cp(wplan, p->plan.wplan.data(), p->plan.wplan.size() * sizeof(double));
+        cp(iplan, p->plan.iplan.data(), p->plan.iplan.size() * sizeof(uint16_t));
+    }
+    return SMM_OK;
+}
+
+void smm_host_plan_free(smm_host_plan *p) { delete p; }
+
+int smm_set_kernel(smm_handle *h, int32_t kernel)
+{
+    if (!h) return fail(SMM_ERR_INVALID, "null handle");
+    if (kernel != 0 && kernel != SMM_KERNEL_STAGED && kernel != SMM_KERNEL_GATHER)
+        return fail(SMM_ERR_INVALID, "kernel must be 0, SMM_KERNEL_STAGED or SMM_KERNEL_GATHER");
+    h->force_kernel = kernel;
+    return SMM_OK;
+}
+
+int64_t smm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char *smm_last_error(void) { return g_err.c_str(); }
+
+const char *smm_version(void) { return "smmregrid_b200 0.1.0 (sm_100a)"; }
+
+}  // extern "C"

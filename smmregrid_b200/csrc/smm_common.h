@@ -1,0 +1,78 @@
+// smm_common.h -- structures shared by the host plan builder, the kernels and the C ABI.
+//
+// Vocabulary (follows the reference / CDO SCRIP files): a *link* is one (src_address,
+// dst_address, remap_matrix[:,0]) triple; a *level* is one weight matrix of a 3-D
+// (mask_dim) weight set; a destination *row* is one dst cell; a *tile* is a run of
+// consecutive destination rows whose source *footprint* (the union of the source columns
+// they touch, widened to aligned *segments*) is staged in shared memory per batch row.
+#pragma once
+#include <cstdint>
+
+namespace smm {
+
+constexpr int kConsumerThreads = 256;               // threads holding links in registers
+constexpr int kConsumerWarps = kConsumerThreads / 32;
+constexpr int kStagedThreads = kConsumerThreads + 32;  // + one TMA producer warp
+constexpr int kMaxStages = 12;
+constexpr int kSegAlign = 8;                        // segment bounds: multiples of 8 elements
+constexpr int kSegGap = 32;                         // merge segments closer than this
+constexpr int kSmemHeader = 256;                    // full[] + empty[] mbarriers
+constexpr int kMaxJobs = 24;                        // levels per grouped launch (by-value args)
+constexpr int kGatherThreads = 256;
+constexpr int kGatherBT = 4;                        // batch rows register-blocked by the gather kernel
+
+struct Seg {          // one aligned run of source columns, in elements
+    uint32_t src;     // first source column
+    uint32_t dst;     // offset inside the staged footprint
+    uint32_t len;     // number of elements
+    uint32_t pad;
+};
+
+struct TileDesc {
+    int32_t row0;     // first destination row
+    int32_t nrows;    // rows in this tile (<= rows_per_tile)
+    int32_t seg0;     // first segment in the level's segment array
+    int32_t nseg;
+    int32_t elems;    // staged footprint, elements (= sum of segment lengths)
+    int32_t pad[3];
+};
+
+// One level of a (possibly grouped) apply.  Passed by value inside JobBatch.
+struct LevelJob {
+    const TileDesc *tiles;
+    const Seg *segs;
+    const double *wplan;      // [ntiles][KPL][256] register image of the link weights
+    const uint16_t *iplan;    // [ntiles][KPL][256] footprint-local element index per link
+    const int32_t *rowptr;    // CSR by destination row, columns ascending (reference order)
+    const int32_t *col;
+    const double *val;
+    const int32_t *imask;     // dst_grid_imask (used when masked)
+    const double *frac;       // dst_grid_frac (used when remap_area_min > 0)
+    const void *x;            // level base of the source slab
+    void *y;                  // level base of the destination slab
+    int32_t nblocks;          // tiles (staged) or row blocks (gather) of this level
+    int32_t item0;            // first work item of this level in the launch
+    int32_t masked;
+    int32_t pad;
+};
+
+struct JobBatch {
+    LevelJob jobs[kMaxJobs];
+    int32_t njobs;
+    int32_t pad;
+};
+
+struct ApplyArgs {
+    int64_t B;            // batch rows per level
+    int64_t x_bstride;    // elements between consecutive batch rows of x
+    int64_t y_bstride;
+    int64_t n_src, n_dst;
+    int64_t chunk;        // batch rows per work item
+    int32_t nchunks;
+    int32_t nstages;
+    uint32_t stage_bytes; // bytes reserved per stage (>= largest footprint, 128-aligned)
+    uint32_t stage_off;   // byte offset of stage 0 in dynamic shared memory
+    double remap_area_min;
+};
+
+}  // namespace smm

@@ -1,0 +1,332 @@
+// smm_kernels.cuh -- sm_100a kernels of the weight-application path.
+//
+//   staged_kernel   Y = X.W for matrices whose tiles have a compact source footprint
+//                   (structured / locally ordered sources).  One producer warp streams the
+//                   tile's footprint of each batch row into shared memory with 1-D TMA bulk
+//                   copies (cp.async.bulk + mbarrier complete_tx, L2 evict-first); eight
+//                   consumer warps hold the tile's link weights and footprint offsets in
+//                   REGISTERS for the whole batch loop, so per batch row the only traffic
+//                   is the X stream itself.  LPR lanes share one destination row.
+//   gather_kernel   generic CSR fallback: direct ld.global.nc gathers, kGatherBT batch rows
+//                   register-blocked per thread (scattered sources, oversized rows,
+//                   unaligned slabs).
+//   mask_sum_kernel mask_tensordot (weights.py:47-52): sequential ascending-src sum per row.
+//
+// Numerics (smmregrid/regrid.py:544-570): non-finite x -> 1e20 in x's dtype, float64
+// products/accumulation, NaN where dst_grid_imask == 0 / dst_grid_frac < remap_area_min /
+// Y > 1e19.  The fast path sums a row's links lane-split + tree-reduced; whenever that sum is
+// within 1e-9 relative of the 1e19 threshold the row is REPLAYED in the reference's order
+// (ascending src, separate multiply and add) so the NaN decision is bit-identical.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "smm_common.h"
+
+namespace smm {
+
+// ------------------------------------------------------------------ PTX helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// 1-D TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes,
+                                             uint32_t bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+
+// ------------------------------------------------------------------ numerics helpers
+
+// regrid.py:545-547: np.ma.fix_invalid + filled -> 1e20 in the input dtype.
+__device__ __forceinline__ float fill_invalid(float v) { return (fabsf(v) <= 3.402823466e+38f) ? v : 1e20f; }
+__device__ __forceinline__ double fill_invalid(double v) { return (fabs(v) <= 1.7976931348623157e+308) ? v : 1e20; }
+
+template <typename TX>
+__device__ __forceinline__ TX ld_nc(const TX *p) { return __ldg(p); }
+
+// Reference-order evaluation of one destination row: links in ascending-src order, separate
+// multiply and add in float64 (pydata/sparse ndarray.COO loop; no FMA contraction).
+template <typename TX>
+__device__ __noinline__ double replay_row(const int32_t *__restrict__ rowptr,
+                                          const int32_t *__restrict__ col,
+                                          const double *__restrict__ val, int row,
+                                          const TX *__restrict__ xrow)
+{
+    double acc = 0.0;
+    const int j1 = rowptr[row + 1];
+    for (int j = rowptr[row]; j < j1; ++j) {
+        const TX v = fill_invalid(xrow[col[j]]);
+        acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(v), val[j]));
+    }
+    return acc;
+}
+
+__device__ __forceinline__ bool near_threshold(double acc) { return fabs(acc - 1e19) <= 1e10; }
+
+template <typename TY>
+__device__ __forceinline__ TY finish(double acc, bool dead)
+{
+    // regrid.py:553-570: imask / frac (folded into `dead`) then `> 1e19 -> NaN`.
+    const double out = (dead || acc > 1e19) ? CUDART_NAN : acc;
+    return static_cast<TY>(out);
+}
+
+__device__ __forceinline__ const LevelJob &find_job(const JobBatch &jb, int item, int &j)
+{
+    j = 0;
+#pragma unroll 1
+    while (j + 1 < jb.njobs && item >= jb.jobs[j + 1].item0) ++j;
+    return jb.jobs[j];
+}
+
+// ------------------------------------------------------------------ staged kernel
+
+template <typename TX, typename TY, int LPR, int KPL>
+__global__ void __launch_bounds__(kStagedThreads, 2)
+staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ ApplyArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    int jidx;
+    const LevelJob &job = find_job(jb, blockIdx.x, jidx);
+    const int local = blockIdx.x - job.item0;
+    const int tile = local % job.nblocks;
+    const int chunk = local / job.nblocks;
+    const int64_t b0 = static_cast<int64_t>(chunk) * a.chunk;
+    const int64_t b1 = (b0 + a.chunk < a.B) ? b0 + a.chunk : a.B;
+    const TileDesc td = job.tiles[tile];
+
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *empty = full + kMaxStages;
+    Seg *ssegs = reinterpret_cast<Seg *>(smem + kSmemHeader);
+    unsigned char *stages = smem + a.stage_off;
+    const int S = a.nstages;
+
+    for (int i = tid; i < td.nseg; i += kStagedThreads) ssegs[i] = job.segs[td.seg0 + i];
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer warp: TMA bulk copies of the footprint, one stage per batch row
+        const uint64_t policy = l2_evict_first_policy();
+        const TX *xbase = static_cast<const TX *>(job.x);
+        const uint32_t tile_bytes = static_cast<uint32_t>(td.elems) * sizeof(TX);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t b = b0; b < b1; ++b) {
+            mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
+            const uint32_t fb = smem_u32(&full[s]);
+            if (lane == 0) mbar_arrive_expect_tx(fb, tile_bytes);
+            __syncwarp();
+            const TX *xrow = xbase + b * a.x_bstride;
+            const uint32_t sbase = smem_u32(stages + static_cast<size_t>(s) * a.stage_bytes);
+            for (int i = lane; i < td.nseg; i += 32) {
+                const Seg sg = ssegs[i];
+                tma_bulk_g2s(sbase + sg.dst * static_cast<uint32_t>(sizeof(TX)), xrow + sg.src,
+                             sg.len * static_cast<uint32_t>(sizeof(TX)), fb, policy);
+            }
+            if (++s == S) { s = 0; ph ^= 1u; }
+        }
+    } else {
+        // ---------------- consumer warps: links live in registers for the whole batch loop
+        const int r_in = tid / LPR;
+        const int l_in = tid % LPR;
+        const int row = td.row0 + r_in;
+        const bool valid = r_in < td.nrows;
+
+        double w[KPL];
+        uint32_t off[KPL];
+        {
+            const size_t base = static_cast<size_t>(tile) * KPL * kConsumerThreads + tid;
+#pragma unroll
+            for (int k = 0; k < KPL; ++k) {
+                w[k] = __ldg(job.wplan + base + static_cast<size_t>(k) * kConsumerThreads);
+                off[k] = static_cast<uint32_t>(__ldg(job.iplan + base + static_cast<size_t>(k) * kConsumerThreads)) *
+                         static_cast<uint32_t>(sizeof(TX));
+            }
+        }
+        bool dead = false;
+        if (valid) {
+            if (job.masked && job.imask[row] == 0) dead = true;
+            if (a.remap_area_min > 0.0 && job.frac[row] < a.remap_area_min) dead = true;
+        }
+        TY *yrow = static_cast<TY *>(job.y) + row;
+        const TX *xbase = static_cast<const TX *>(job.x);
+
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t b = b0; b < b1; ++b) {
+            mbar_wait(smem_u32(&full[s]), ph);
+            const unsigned char *st = stages + static_cast<size_t>(s) * a.stage_bytes;
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+            for (int k = 0; k < KPL; k += 4) {
+                const TX v0 = fill_invalid(*reinterpret_cast<const TX *>(st + off[k + 0]));
+                const TX v1 = fill_invalid(*reinterpret_cast<const TX *>(st + off[k + 1]));
+                const TX v2 = fill_invalid(*reinterpret_cast<const TX *>(st + off[k + 2]));
+                const TX v3 = fill_invalid(*reinterpret_cast<const TX *>(st + off[k + 3]));
+                acc0 = fma(static_cast<double>(v0), w[k + 0], acc0);
+                acc1 = fma(static_cast<double>(v1), w[k + 1], acc1);
+                acc2 = fma(static_cast<double>(v2), w[k + 2], acc2);
+                acc3 = fma(static_cast<double>(v3), w[k + 3], acc3);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&empty[s]));   // stage may be refilled
+            double acc = (acc0 + acc1) + (acc2 + acc3);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (l_in == 0 && valid) {
+                if (near_threshold(acc))
+                    acc = replay_row<TX>(job.rowptr, job.col, job.val, row, xbase + b * a.x_bstride);
+                yrow[b * a.y_bstride] = finish<TY>(acc, dead);
+            }
+            if (++s == S) { s = 0; ph ^= 1u; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ gather kernel
+
+template <typename TX, typename TY, int LPR>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ ApplyArgs a)
+{
+    constexpr int BT = kGatherBT;
+    constexpr int RPB = kGatherThreads / LPR;   // destination rows per block
+    int jidx;
+    const LevelJob &job = find_job(jb, blockIdx.x, jidx);
+    const int local = blockIdx.x - job.item0;
+    const int rblock = local % job.nblocks;
+    const int chunk = local / job.nblocks;
+    const int64_t b0 = static_cast<int64_t>(chunk) * a.chunk;
+    const int64_t b1 = (b0 + a.chunk < a.B) ? b0 + a.chunk : a.B;
+
+    const int tid = threadIdx.x;
+    const int l_in = tid % LPR;
+    const int64_t row64 = static_cast<int64_t>(rblock) * RPB + tid / LPR;
+    const bool valid = row64 < a.n_dst;
+    const int row = valid ? static_cast<int>(row64) : 0;
+
+    int j0 = 0, j1 = 0;
+    bool dead = false;
+    if (valid) {
+        j0 = job.rowptr[row];
+        j1 = job.rowptr[row + 1];
+        if (job.masked && job.imask[row] == 0) dead = true;
+        if (a.remap_area_min > 0.0 && job.frac[row] < a.remap_area_min) dead = true;
+    }
+    const TX *xbase = static_cast<const TX *>(job.x);
+    TY *yrow = static_cast<TY *>(job.y) + row;
+
+    for (int64_t b = b0; b < b1; b += BT) {
+        const TX *xr[BT];
+#pragma unroll
+        for (int t = 0; t < BT; ++t) {
+            const int64_t bb = (b + t < b1) ? b + t : b1 - 1;
+            xr[t] = xbase + bb * a.x_bstride;
+        }
+        double acc[BT];
+#pragma unroll
+        for (int t = 0; t < BT; ++t) acc[t] = 0.0;
+        for (int j = j0 + l_in; j < j1; j += LPR) {
+            const int c = __ldg(job.col + j);
+            const double wv = __ldg(job.val + j);
+            TX v[BT];
+#pragma unroll
+            for (int t = 0; t < BT; ++t) v[t] = ld_nc(xr[t] + c);
+#pragma unroll
+            for (int t = 0; t < BT; ++t)
+                acc[t] = fma(static_cast<double>(fill_invalid(v[t])), wv, acc[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < BT; ++t) {
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+        }
+        if (l_in == 0 && valid) {
+#pragma unroll
+            for (int t = 0; t < BT; ++t) {
+                if (b + t < b1) {
+                    double r = acc[t];
+                    if (near_threshold(r)) r = replay_row<TX>(job.rowptr, job.col, job.val, row, xr[t]);
+                    yrow[(b + t) * a.y_bstride] = finish<TY>(r, dead);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ mask_tensordot
+
+// weights.py:47-52.  One thread per destination row, links in ascending-src order, separate
+// multiply and add: bit-identical to the reference's accumulation, so `t < 0.5` is too.
+__global__ void mask_sum_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                const double *__restrict__ val, const int32_t *__restrict__ src_imask,
+                                int32_t *__restrict__ dst_imask, int32_t *__restrict__ any_masked,
+                                int64_t n_dst)
+{
+    const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (row >= n_dst) return;
+    double t = 0.0;
+    const int j1 = rowptr[row + 1];
+    for (int j = rowptr[row]; j < j1; ++j)
+        t = __dadd_rn(t, __dmul_rn(static_cast<double>(src_imask[col[j]]), val[j]));
+    const int32_t m = t < 0.5 ? 0 : 1;
+    dst_imask[row] = m;
+    if (m == 0) atomicOr(any_masked, 1);
+}
+
+}  // namespace smm

@@ -1,0 +1,48 @@
+// smm_plan.h -- host-side construction of the device operator from CDO link arrays.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "smm_common.h"
+
+namespace smm {
+
+// CSR by destination row with ascending source columns and summed duplicates: the per-row
+// view of what sparse.COO(coords=[src,dst], data) holds (smmregrid/weights.py:37-39).
+struct HostCsr {
+    int64_t n_src = 0, n_dst = 0;
+    std::vector<int32_t> rowptr;   // n_dst + 1
+    std::vector<int32_t> col;
+    std::vector<double> val;
+    int32_t max_row_nnz = 0;
+    int64_t touched_src = 0;
+};
+
+// Returns 0 on success, SMM_ERR_* otherwise (message in err).
+int build_csr(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t *src_address,
+              const int32_t *dst_address, const double *remap_matrix, int32_t num_wgts,
+              int32_t index_base, HostCsr &out, std::string &err);
+
+// Tile plan of the staged kernel.
+struct HostPlan {
+    bool ok = false;          // false: level is served by the gather kernel only
+    std::string why;          // reason when !ok
+    int32_t lpr = 0, kpl = 0, rows_per_tile = 0;
+    std::vector<TileDesc> tiles;
+    std::vector<Seg> segs;
+    std::vector<double> wplan;     // [ntiles][kpl][256]
+    std::vector<uint16_t> iplan;   // [ntiles][kpl][256]
+    int32_t max_tile_segments = 0;
+    int64_t max_tile_elems = 0;
+    int64_t sum_tile_elems = 0;
+};
+
+// Picks (lanes per row, links per lane) for a maximum row length; false if no staged
+// configuration can hold it.
+bool choose_lanes(int32_t max_row_nnz, int32_t &lpr, int32_t &kpl);
+
+// force_lpr/force_kpl > 0 impose a configuration shared by all levels of a 3-D weight set.
+void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, HostPlan &plan);
+
+}  // namespace smm

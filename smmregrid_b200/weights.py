@@ -1,0 +1,312 @@
+"""Weight handling -- host-side mirror of ``smmregrid/weights.py`` over the C ABI.
+
+Same function names and argument meaning as the reference
+(``compute_weights_matrix``, ``compute_weights_matrix3d``, ``mask_tensordot``,
+``mask_weights``, ``check_mask``); the "weights matrix" they pass around is a
+:class:`WeightsMatrix`, a device-resident operator handle, instead of a lazy ``sparse.COO``.
+Every caller in the reference treats that object as opaque (only ``[level]`` indexing for
+3-D weights, ``regrid.py:404``), which is what makes the substitution a drop-in.
+
+The *weights dataset* consumed here is the SCRIP-style file CDO writes
+(``cdo gen<method>``): a :class:`CdoWeights` wraps a mapping of numpy arrays with the same
+variable names, or an ``xarray.Dataset`` when xarray is installed.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Mapping, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+LINK_DIMS = ("numLinks", "num_links")          # CDO 2.2.0 renamed it (weights.py:13)
+
+
+class CdoWeights:
+    """Minimal stand-in for the ``xarray.Dataset`` of CDO weights.
+
+    Variables (numpy arrays, CDO names): ``src_address``, ``dst_address`` (1-based int32),
+    ``remap_matrix`` [num_links, num_wgts] float64, ``src_grid_imask``, ``dst_grid_imask``,
+    ``dst_grid_frac``, ``src_grid_dims``, ``dst_grid_dims``, ``dst_grid_center_lat/lon``
+    (radians), optional ``link_length`` [L] + a leading level axis on the per-link and
+    per-cell arrays for 3-D weights (``cdogenerate.py:310-343``), optional
+    ``dst_grid_masked``.  ``levels`` holds the coordinate values of ``mask_dim``.
+    """
+
+    def __init__(self, variables: Mapping[str, np.ndarray], attrs: Optional[dict] = None,
+                 mask_dim: Optional[str] = None, levels: Optional[Sequence[float]] = None):
+        self.vars = {k: np.asarray(v) for k, v in variables.items()}
+        self.attrs = dict(attrs or {})
+        self.mask_dim = mask_dim
+        self.levels = None if levels is None else np.asarray(levels, dtype=np.float64)
+        if "link_length" in self.vars and self.levels is None:
+            self.levels = np.arange(self.vars["link_length"].size, dtype=np.float64)
+            self.mask_dim = mask_dim or "lev"
+
+    # --- construction helpers -------------------------------------------------------
+    @classmethod
+    def from_any(cls, obj, mask_dim=None) -> "CdoWeights":
+        if isinstance(obj, CdoWeights):
+            return obj
+        if isinstance(obj, Mapping):
+            return cls(obj, mask_dim=mask_dim)
+        if isinstance(obj, str):
+            return cls.from_file(obj, mask_dim=mask_dim)
+        if hasattr(obj, "data_vars") and hasattr(obj, "attrs"):      # xarray.Dataset
+            variables = {k: np.asarray(v.values) for k, v in obj.variables.items()}
+            levels = None
+            md = mask_dim
+            if "link_length" in obj.variables:
+                md = md or obj["link_length"].dims[0]
+                levels = np.asarray(obj[md].values, dtype=np.float64) if md in obj.coords else None
+            return cls(variables, attrs=dict(obj.attrs), mask_dim=md, levels=levels)
+        raise TypeError(f"cannot interpret {type(obj).__name__} as CDO weights")
+
+    @classmethod
+    def from_file(cls, path: str, mask_dim=None) -> "CdoWeights":
+        """``.npz`` archive, or netCDF-3 classic via ``scipy.io.netcdf_file`` (netCDF-4 needs
+        xarray + netCDF4, then pass the opened Dataset)."""
+        if path.endswith(".npz"):
+            with np.load(path, allow_pickle=False) as z:
+                variables = {k: z[k] for k in z.files if not k.startswith("__attr__")}
+                attrs = {k[len("__attr__"):]: str(z[k]) for k in z.files if k.startswith("__attr__")}
+            levels = variables.pop("__levels__", None)
+            return cls(variables, attrs=attrs, mask_dim=mask_dim, levels=levels)
+        from scipy.io import netcdf_file
+        with netcdf_file(path, "r", mmap=False) as nc:
+            variables = {k: np.array(v[...]) for k, v in nc.variables.items()}
+            attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in nc._attributes.items()}
+        return cls(variables, attrs=attrs, mask_dim=mask_dim)
+
+    def save_npz(self, path: str):
+        out = dict(self.vars)
+        for k, v in self.attrs.items():
+            out["__attr__" + k] = np.asarray(str(v))
+        if self.levels is not None:
+            out["__levels__"] = self.levels
+        np.savez(path, **out)
+
+    # --- dataset-like access ----------------------------------------------------------
+    def __getitem__(self, name):
+        return self.vars[name]
+
+    def __contains__(self, name):
+        return name in self.vars
+
+    def assign(self, **kw) -> "CdoWeights":
+        """Copy with some variables replaced (xarray ``Dataset.assign``, weights.py:78,82)."""
+        new = dict(self.vars)
+        new.update({k: np.asarray(v) for k, v in kw.items()})
+        return CdoWeights(new, self.attrs, self.mask_dim, self.levels)
+
+    @property
+    def is3d(self) -> bool:
+        return "link_length" in self.vars
+
+    @property
+    def n_levels(self) -> int:
+        return int(self.vars["link_length"].size) if self.is3d else 1
+
+    @property
+    def sizes(self):
+        """``src_grid_size`` / ``dst_grid_size`` as the reference reads them (weights.py:34)."""
+        n_src = int(np.prod(self.vars["src_grid_dims"])) if "src_grid_dims" in self.vars \
+            else int(self.vars["src_grid_imask"].shape[-1])
+        n_dst = int(np.prod(self.vars["dst_grid_dims"])) if "dst_grid_dims" in self.vars \
+            else int(self.vars["dst_grid_imask"].shape[-1])
+        return {"src_grid_size": n_src, "dst_grid_size": n_dst}
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _device_index(device) -> int:
+    if device is None:
+        try:
+            import torch
+            return torch.cuda.current_device() if torch.cuda.is_available() else 0
+        except Exception:
+            return 0
+    if isinstance(device, int):
+        return device
+    s = str(device)
+    if s == "cuda":
+        return _device_index(None)
+    if s.startswith("cuda:"):
+        return int(s.split(":", 1)[1])
+    raise ValueError(f"smmregrid_b200 runs on CUDA devices only, got device={device!r}")
+
+
+class WeightsMatrix:
+    """Device operator handle: what ``compute_weights_matrix*`` returns.
+
+    ``wm[level]`` gives a per-level view like indexing the reference's list of matrices
+    (``regrid.py:404``).  Holds the per-level ``dst_grid_imask`` / ``dst_grid_frac`` on the
+    device once installed.
+    """
+
+    def __init__(self, handle, n_levels: int, device: int, n_src: int, n_dst: int):
+        self._h = handle
+        self.n_levels = n_levels
+        self.device = device
+        self.shape = (n_src, n_dst)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().smm_destroy(h)
+            except Exception:
+                pass
+
+    def close(self):
+        self.__del__()
+
+    def __len__(self):
+        return self.n_levels
+
+    def __getitem__(self, level: int) -> "LevelView":
+        if not -self.n_levels <= level < self.n_levels:
+            raise IndexError(level)
+        return LevelView(self, level % self.n_levels)
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("WeightsMatrix was closed")
+        return self._h
+
+    def info(self, level: int = 0) -> dict:
+        inf = _lib.SmmInfo()
+        _lib.check(_lib.load().smm_get_info(self.handle, level, ctypes.byref(inf)))
+        return inf.asdict()
+
+    def set_dst_mask(self, level: int, dst_grid_imask=None, dst_grid_frac=None):
+        im = None if dst_grid_imask is None else np.ascontiguousarray(dst_grid_imask, dtype=np.int32).ravel()
+        fr = None if dst_grid_frac is None else np.ascontiguousarray(dst_grid_frac, dtype=np.float64).ravel()
+        for a in (im, fr):
+            if a is not None and a.size != self.shape[1]:
+                raise ValueError(f"expected {self.shape[1]} destination cells, got {a.size}")
+        _lib.check(_lib.load().smm_set_dst_mask(self.handle, level, _ptr(im), _ptr(fr)))
+
+    def set_kernel(self, kernel: Optional[str]):
+        code = {None: 0, "auto": 0, "staged": _lib.SMM_KERNEL_STAGED, "gather": _lib.SMM_KERNEL_GATHER}[kernel]
+        _lib.check(_lib.load().smm_set_kernel(self.handle, code))
+
+
+class LevelView:
+    def __init__(self, parent: WeightsMatrix, level: int):
+        self.parent, self.level = parent, level
+        self.shape = parent.shape
+
+
+def _as_matrix_level(matrix):
+    if isinstance(matrix, LevelView):
+        return matrix.parent, matrix.level
+    if isinstance(matrix, WeightsMatrix):
+        return matrix, 0
+    raise TypeError("expected a WeightsMatrix (or a level of one)")
+
+
+def compute_weights_matrix(weights, device=None) -> WeightsMatrix:
+    """Convert CDO weights to a device operator (reference: ``weights.py:25-44``).
+
+    ``src_address - 1``, ``dst_address - 1`` and ``remap_matrix[:, 0]`` become a CSR by
+    destination row; duplicate links are summed as ``sparse.COO`` does.
+    """
+    w = CdoWeights.from_any(weights)
+    src = np.ascontiguousarray(w["src_address"], dtype=np.int32).ravel()
+    dst = np.ascontiguousarray(w["dst_address"], dtype=np.int32).ravel()
+    rm = np.ascontiguousarray(w["remap_matrix"], dtype=np.float64)
+    num_wgts = rm.shape[-1] if rm.ndim == 2 else 1
+    if rm.size != src.size * num_wgts or dst.size != src.size:
+        raise ValueError("src_address, dst_address and remap_matrix disagree on the number of links")
+    n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+    dev = _device_index(device)
+    h = ctypes.c_void_p()
+    _lib.check(_lib.load().smm_create(n_src, n_dst, src.size, _ptr(src), _ptr(dst), _ptr(rm),
+                                     num_wgts, 1, dev, ctypes.byref(h)))
+    wm = WeightsMatrix(h, 1, dev, n_src, n_dst)
+    _install_masks(wm, w)
+    return wm
+
+
+def compute_weights_matrix3d(weights, mask_dim="lev", device=None) -> WeightsMatrix:
+    """Per-level operators from padded 3-D weights (reference: ``weights.py:7-23``): level i
+    uses links ``[0:link_length[i])``."""
+    w = CdoWeights.from_any(weights, mask_dim=mask_dim)
+    ll = np.ascontiguousarray(w["link_length"], dtype=np.int64).ravel()
+    L = ll.size
+    src = np.ascontiguousarray(w["src_address"], dtype=np.int32).reshape(L, -1)
+    dst = np.ascontiguousarray(w["dst_address"], dtype=np.int32).reshape(L, -1)
+    nl_max = src.shape[1]
+    rm = np.ascontiguousarray(w["remap_matrix"], dtype=np.float64).reshape(L, nl_max, -1)
+    num_wgts = rm.shape[2]
+    n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+    dev = _device_index(device)
+    h = ctypes.c_void_p()
+    _lib.check(_lib.load().smm_create_levels(L, _ptr(ll), nl_max, n_src, n_dst, _ptr(src), _ptr(dst),
+                                            _ptr(rm), num_wgts, 1, dev, ctypes.byref(h)))
+    wm = WeightsMatrix(h, L, dev, n_src, n_dst)
+    _install_masks(wm, w)
+    return wm
+
+
+def _install_masks(wm: WeightsMatrix, w: CdoWeights):
+    """Upload dst_grid_imask / dst_grid_frac per level (what apply_weights reads, regrid.py:506-508).
+    Non-conservative 3-D weights carry a single 2-D dst_grid_frac reused by every level
+    (cdogenerate.py:324-328)."""
+    n_dst = wm.shape[1]
+    im = w.vars.get("dst_grid_imask")
+    fr = w.vars.get("dst_grid_frac")
+    for lev in range(wm.n_levels):
+        iml = frl = None
+        if im is not None:
+            iml = im.reshape(-1, n_dst)[lev if im.size > n_dst else 0]
+        if fr is not None:
+            frl = fr.reshape(-1, n_dst)[lev if fr.size > n_dst else 0]
+        if iml is not None or frl is not None:
+            wm.set_dst_mask(lev, iml, frl)
+
+
+def mask_tensordot(src_mask, weights_matrix) -> np.ndarray:
+    """Apply the operator to a source mask and threshold at 0.5 (reference: ``weights.py:47-52``).
+    Returns the destination mask (int32 0/1) and installs it on the level."""
+    wm, level = _as_matrix_level(weights_matrix)
+    sm = np.ascontiguousarray(src_mask, dtype=np.int32).ravel()
+    if sm.size != wm.shape[0]:
+        raise ValueError(f"expected {wm.shape[0]} source cells, got {sm.size}")
+    out = np.empty(wm.shape[1], dtype=np.int32)
+    flag = ctypes.c_int32(0)
+    _lib.check(_lib.load().smm_mask_sum(wm.handle, level, _ptr(sm), _ptr(out), ctypes.byref(flag)))
+    return out
+
+
+def mask_weights(weights, weights_matrix, mask_dim=None) -> CdoWeights:
+    """Precompute the target mask, 2-D or per level (reference: ``weights.py:55-84``).
+    Returns a copy of the weights with ``dst_grid_imask`` replaced; the device operator is
+    updated too."""
+    w = CdoWeights.from_any(weights, mask_dim=mask_dim)
+    n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+    src_mask = w["src_grid_imask"]
+    if mask_dim is not None:
+        L = w.n_levels
+        sm = src_mask.reshape(L, n_src)
+        levels = [mask_tensordot(sm[i], weights_matrix[i]) for i in range(L)]
+        dst_mask = np.stack(levels, axis=0).reshape((L,) + w["dst_grid_imask"].shape[1:])
+    else:
+        dst_mask = mask_tensordot(src_mask.reshape(n_src), weights_matrix).reshape(w["dst_grid_imask"].shape)
+    return w.assign(dst_grid_imask=dst_mask)
+
+
+def check_mask(weights, mask_dim=None):
+    """True where the target mask is not all ones (reference: ``weights.py:103-120``): a bool
+    for 2-D weights, bool[L] when ``mask_dim`` is given."""
+    w = CdoWeights.from_any(weights, mask_dim=mask_dim)
+    wdst = w["dst_grid_imask"]
+    if mask_dim is not None:
+        L = w.n_levels
+        return ~(wdst.reshape(L, -1) == 1).all(axis=1)
+    return bool(~(wdst == 1).all())

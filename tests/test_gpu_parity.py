@@ -1,0 +1,309 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI, against the CPU oracle.
+
+Bar: bit-exact NaN pattern; values within 1e-12 relative for float64 output
+and 1e-6 relative for float32 output.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import assert_parity, random_links
+
+pytestmark = pytest.mark.gpu
+
+RTOL_F64 = 1e-12
+RTOL_F32 = 1e-6
+
+
+def _create(lib, src, dst, rm, n_src, n_dst):
+    from smmregrid_b200 import _lib
+    h = ctypes.c_void_p()
+    src = np.ascontiguousarray(src, np.int32)
+    dst = np.ascontiguousarray(dst, np.int32)
+    rm = np.ascontiguousarray(rm, np.float64)
+    _lib.check(lib.smm_create(n_src, n_dst, src.size, src.ctypes.data, dst.ctypes.data, rm.ctypes.data,
+                              rm.shape[1], 1, 0, ctypes.byref(h)))
+    return h
+
+
+def _apply(lib, h, x_np, n_dst, ydtype, masked, amin, imask=None, frac=None, kernel=0, level=0):
+    import torch
+    from smmregrid_b200 import _lib
+    if imask is not None or frac is not None:
+        im = None if imask is None else np.ascontiguousarray(imask, np.int32)
+        fr = None if frac is None else np.ascontiguousarray(frac, np.float64)
+        _lib.check(lib.smm_set_dst_mask(h, level, None if im is None else im.ctypes.data,
+                                        None if fr is None else fr.ctypes.data))
+    _lib.check(lib.smm_set_kernel(h, kernel))
+    x = torch.from_numpy(x_np).cuda()
+    B = x.shape[0]
+    y = torch.full((B, n_dst), -7.0, dtype=torch.float64 if ydtype == np.float64 else torch.float32, device="cuda")
+    _lib.check(lib.smm_apply(h, level, x.data_ptr(), 0 if x_np.dtype == np.float32 else 1, B, x.shape[1],
+                             y.data_ptr(), 1 if ydtype == np.float64 else 0, n_dst, int(masked), float(amin),
+                             torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return y.cpu().numpy()
+
+
+def _info(lib, h, level=0):
+    from smmregrid_b200 import _lib
+    inf = _lib.SmmInfo()
+    _lib.check(lib.smm_get_info(h, level, ctypes.byref(inf)))
+    return inf.asdict()
+
+
+@pytest.mark.parametrize("xdt", [np.float32, np.float64])
+@pytest.mark.parametrize("ydt", [np.float64, np.float32])
+@pytest.mark.parametrize("kernel", [0, 2])
+@pytest.mark.parametrize("nnz_per_row", [1, 3, 7, 12, 30, 60, 120, 200])
+def test_random_matrix(smm_lib, oracle, cuda, xdt, ydt, kernel, nnz_per_row):
+    """Random links over a locally ordered source: every lane configuration, both kernels."""
+    rng = np.random.default_rng(100 + nnz_per_row)
+    n_src, n_dst, B = 4096, 700, 37
+    counts = rng.integers(0, nnz_per_row + 1, size=n_dst)
+    counts[5] = nnz_per_row                      # pin the lane configuration
+    dst = np.repeat(np.arange(n_dst), counts)
+    centre = (dst * n_src) // n_dst
+    src = np.clip(centre + rng.integers(-300, 300, size=dst.size), 0, n_src - 1)
+    w = rng.random(dst.size)
+    o = np.lexsort((src, dst))
+    src, dst, w = src[o] + 1, dst[o] + 1, w[o].reshape(-1, 1)
+    x = (280 + 20 * rng.standard_normal((B, n_src))).astype(xdt)
+    x[rng.random(x.shape) < 0.02] = np.nan
+    x[3, 100] = np.inf
+    x[4, 200] = -np.inf
+    imask = (rng.random(n_dst) > 0.1).astype(np.int32)
+    frac = rng.random(n_dst)
+    mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, imask, frac, 0.5, True)
+    h = _create(smm_lib, src, dst, w, n_src, n_dst)
+    try:
+        y = _apply(smm_lib, h, x, n_dst, ydt, True, 0.5, imask, frac, kernel)
+        if ydt == np.float32:
+            y_ref = y_ref.astype(np.float32)
+        assert_parity(y, y_ref, RTOL_F64 if ydt == np.float64 else RTOL_F32, f"nnz{nnz_per_row}")
+    finally:
+        smm_lib.smm_destroy(h)
+
+
+@pytest.mark.parametrize("cfg,scale,B", [("C1", 1, 12), ("C2", 4, 40), ("C4", 5, 24), ("C4", 10, 130)])
+@pytest.mark.parametrize("nan_mode", ["none", "static", "step"])
+def test_named_configs(smm_lib, oracle, cuda, cfg, scale, B, nan_mode):
+    """BASELINE.json configurations at reduced size, float32 in, float64 and float32 out."""
+    from smmregrid_b200 import synth
+    w = synth.config_weights(cfg, scale)
+    n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+    x = synth.synthetic_field((B, n_src), np.float32, seed=5, nan_mode=nan_mode)
+    mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    imask, _ = oracle.mask_tensordot_c(w["src_grid_imask"], mat)
+    y_ref = oracle.apply_weights_c(x, mat, imask, w["dst_grid_frac"], 0.5, True, nthreads=4)
+    h = _create(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    try:
+        assert _info(smm_lib, h)["kernel_name"] == "staged"
+        for kernel in (0, 2):
+            y = _apply(smm_lib, h, x, n_dst, np.float64, True, 0.5, imask, w["dst_grid_frac"], kernel)
+            assert_parity(y, y_ref, RTOL_F64, f"{cfg} f64 kernel{kernel}")
+        y32 = _apply(smm_lib, h, x, n_dst, np.float32, True, 0.5, imask, w["dst_grid_frac"], 0)
+        assert_parity(y32, y_ref.astype(np.float32), RTOL_F32, f"{cfg} f32")
+    finally:
+        smm_lib.smm_destroy(h)
+
+
+def test_mask_sum_matches_oracle(smm_lib, oracle, cuda):
+    """mask_tensordot: bit-exact 0/1 destination mask, including sums that land on 0.5."""
+    from smmregrid_b200 import _lib, synth
+    w = synth.conservative_latlon(360, 180, 36, 18)
+    n_src, n_dst = 360 * 180, 36 * 18
+    rng = np.random.default_rng(3)
+    src_mask = (rng.random(n_src) > 0.5).astype(np.int32)
+    src_mask[: n_src // 3] = 0
+    mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    ref, _ = oracle.mask_tensordot_c(src_mask, mat)
+    h = _create(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    try:
+        out = np.empty(n_dst, np.int32)
+        flag = ctypes.c_int32(-1)
+        _lib.check(smm_lib.smm_mask_sum(h, 0, src_mask.ctypes.data, out.ctypes.data, ctypes.byref(flag)))
+        assert np.array_equal(out, ref)
+        assert flag.value == int((ref == 0).any())
+    finally:
+        smm_lib.smm_destroy(h)
+
+
+def test_threshold_replay_is_reference_order(smm_lib, oracle, cuda):
+    """Rows whose filled sum lands within rounding of 1e19: the NaN decision must be the
+    reference's (ascending-src order, separate multiply and add), not the tree order's."""
+    rng = np.random.default_rng(9)
+    n_src, n_dst, B = 2048, 512, 16
+    k = 40
+    dst = np.repeat(np.arange(n_dst), k)
+    src = (np.repeat(np.arange(n_dst) * 3, k) + np.tile(np.arange(k), n_dst)) % n_src
+    w = np.full(dst.size, 1.0 / k)
+    w += rng.uniform(-1e-17, 1e-17, size=w.size)         # perturb the last bits
+    o = np.lexsort((src, dst))
+    src, dst, w = src[o] + 1, dst[o] + 1, w[o].reshape(-1, 1)
+    x = rng.uniform(0, 2000, size=(B, n_src))          # float64: the fill is exactly 1e20
+    # exactly 4 of 40 links NaN -> filled sum = 0.1 * 1e20 +- rounding, right at the threshold
+    for d in range(n_dst):
+        cols = (d * 3 + rng.choice(k, size=4, replace=False)) % n_src
+        x[d % B, cols] = np.nan
+    mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False)
+    assert 0 < np.isnan(y_ref).sum() < y_ref.size
+    h = _create(smm_lib, src, dst, w, n_src, n_dst)
+    try:
+        for kernel in (0, 2):
+            y = _apply(smm_lib, h, x, n_dst, np.float64, False, 0.0, kernel=kernel)
+            assert np.array_equal(np.isnan(y), np.isnan(y_ref)), kernel
+            near = np.abs(y_ref - 1e19) < 1e10
+            assert near.any()
+            assert np.array_equal(y[near], y_ref[near]), "replayed rows must be bit-identical"
+    finally:
+        smm_lib.smm_destroy(h)
+
+
+def test_reference_quirks(smm_lib, oracle, cuda):
+    """0.05-weight NaN leaks 5e18; negative weights never trip; > 1e19 data -> NaN;
+    identity weights are exact; all-NaN row -> all-NaN; only column 0 of remap_matrix is used."""
+    n = 64
+    src = np.arange(1, n + 1, dtype=np.int32)
+    dst = src.copy()
+    rm = np.ones((n, 3))
+    rm[:, 1:] = 99.0
+    rm[0, 0] = 0.05
+    rm[1, 0] = -0.5
+    x = np.linspace(1, 2, 3 * n, dtype=np.float32).reshape(3, n)
+    x[0, 0] = np.nan
+    x[0, 1] = np.nan
+    x[1, 5] = 3e19
+    x[2, :] = np.nan
+    mat = oracle.compute_weights_matrix_c(src, dst, rm, n, n)
+    y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False)
+    h = _create(smm_lib, src, dst, rm, n, n)
+    try:
+        y = _apply(smm_lib, h, x, n, np.float64, False, 0.0)
+    finally:
+        smm_lib.smm_destroy(h)
+    assert np.array_equal(np.isnan(y), np.isnan(y_ref))
+    assert y[0, 0] == np.float64(np.float32(1e20)) * 0.05 and np.isfinite(y[0, 0])
+    assert y[0, 1] == np.float64(np.float32(1e20)) * -0.5
+    assert np.isnan(y[1, 5])
+    assert np.isnan(y[2, 2:]).all()
+    assert np.array_equal(y[1, 6:], x[1, 6:].astype(np.float64))
+
+
+def test_levels_grouped_apply(smm_lib, oracle, cuda):
+    """3-D ocean weights: one grouped launch over all levels == per-level oracle; subset of
+    levels == slicing the full result (tests/levels_test.py in the reference)."""
+    import torch
+    from smmregrid_b200 import Regridder, synth
+    w = synth.ocean3d_weights(72, 36, 36, 18, n_levels=30)
+    n_src, n_dst, L, T = 72 * 36, 36 * 18, 30, 5
+    x = synth.synthetic_field((T, L, n_src), np.float32, seed=2)
+    x[:, w["src_grid_imask"] == 0] = np.nan
+    mats = oracle.compute_weights_matrix3d_np(w["src_address"], w["dst_address"], w["remap_matrix"],
+                                              w["link_length"], n_src, n_dst,
+                                              builder=oracle.compute_weights_matrix_c)
+    imask = np.stack([oracle.mask_tensordot_c(w["src_grid_imask"][l], mats[l])[0] for l in range(L)])
+    masked = oracle.check_mask_np(imask)
+    y_ref = oracle.regrid3d_np(x, 1, w.levels, w.levels, mats, imask, w["dst_grid_frac"], masked, 0.5)
+    rg = Regridder(weights=w, remap_area_min=0.5)
+    assert np.array_equal(np.asarray(rg.masked), masked)
+    assert np.array_equal(rg.weights["dst_grid_imask"], imask)
+    y = rg.regrid(torch.from_numpy(x).cuda()).cpu().numpy().reshape(T, L, n_dst)
+    assert_parity(y, y_ref, RTOL_F64, "3d")
+    sel = [14, 15, 17]
+    ys = rg.regrid(x[:, sel], levels=w.levels[sel]).reshape(T, len(sel), n_dst)
+    assert_parity(ys, y_ref[:, sel], RTOL_F64, "3d subset")
+    with pytest.raises(ValueError):
+        rg.regrid(x[:, :2], levels=[1e9, 2e9])
+    # transpose=False keeps the level axis first (regrid.py:410)
+    rg2 = Regridder(weights=w, remap_area_min=0.5, transpose=False)
+    y2 = rg2.regrid(x).reshape(L, T, n_dst)
+    assert_parity(np.moveaxis(y2, 0, 1), y_ref, RTOL_F64, "3d no transpose")
+
+
+def test_host_apply_and_strides(smm_lib, oracle, cuda):
+    """smm_apply_host (chunked H2D/D2H pipeline) and non-trivial ldx/ldy."""
+    import torch
+    from smmregrid_b200 import _lib, synth
+    w = synth.config_weights("C2", 8)
+    n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+    B = 101
+    x = synth.synthetic_field((B, n_src), np.float32, seed=8, nan_mode="random")
+    mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, None, w["dst_grid_frac"], 0.5, False, nthreads=4)
+    h = _create(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    try:
+        fr = np.ascontiguousarray(w["dst_grid_frac"], np.float64)
+        _lib.check(smm_lib.smm_set_dst_mask(h, 0, None, fr.ctypes.data))
+        y = np.zeros((B, n_dst), np.float64)
+        _lib.check(smm_lib.smm_apply_host(h, 0, x.ctypes.data, 0, B, n_src, y.ctypes.data, 1, n_dst, 0, 0.5, 16))
+        assert_parity(y, y_ref, RTOL_F64, "host")
+        # padded strides on the device path (ldx = n_src + 4 keeps 16-byte rows for TMA)
+        xp = torch.zeros((B, n_src + 4), dtype=torch.float32, device="cuda")
+        xp[:, :n_src] = torch.from_numpy(x).cuda()
+        yp = torch.full((B, n_dst + 3), 5.0, dtype=torch.float64, device="cuda")
+        _lib.check(smm_lib.smm_apply(h, 0, xp.data_ptr(), 0, B, n_src + 4, yp.data_ptr(), 1, n_dst + 3, 0, 0.5, None))
+        torch.cuda.synchronize()
+        assert_parity(yp[:, :n_dst].cpu().numpy(), y_ref, RTOL_F64, "strided")
+        assert (yp[:, n_dst:] == 5.0).all()
+        # odd ldx breaks the 16-byte row alignment: must still be right (gather kernel)
+        xo = torch.zeros((B, n_src + 1), dtype=torch.float32, device="cuda")
+        xo[:, :n_src] = torch.from_numpy(x).cuda()
+        yo = torch.empty((B, n_dst), dtype=torch.float64, device="cuda")
+        _lib.check(smm_lib.smm_apply(h, 0, xo.data_ptr(), 0, B, n_src + 1, yo.data_ptr(), 1, n_dst, 0, 0.5, None))
+        torch.cuda.synchronize()
+        assert_parity(yo.cpu().numpy(), y_ref, RTOL_F64, "unaligned")
+    finally:
+        smm_lib.smm_destroy(h)
+
+
+def test_full_size_properties(smm_lib, cuda):
+    """C4 at full grid size (6.48 M -> 64 800, 7.1 M links): size-independent properties.
+    Constant field -> constant (rows sum to 1); linearity; NaN step -> NaN row; staged == gather."""
+    import torch
+    from smmregrid_b200 import Regridder, synth
+    w = synth.config_weights("C4")
+    rg = Regridder(weights=w, remap_area_min=0.5)
+    n_src, n_dst = rg.n_src, rg.n_dst
+    assert rg.weights_matrix.info()["kernel_name"] == "staged"
+    B = 48
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x1 = 280 + 20 * torch.randn((B, n_src), generator=g, device="cuda", dtype=torch.float32)
+    x2 = 5 * torch.randn((B, n_src), generator=g, device="cuda", dtype=torch.float32)
+    const = torch.full((2, n_src), 3.25, device="cuda", dtype=torch.float32)
+    yc = rg.regrid(const).reshape(2, n_dst)
+    assert torch.allclose(yc, torch.full_like(yc, 3.25), rtol=1e-13, atol=0)
+    y1 = rg.regrid(x1).reshape(B, n_dst)
+    y2 = rg.regrid(x2).reshape(B, n_dst)
+    y12 = rg.regrid((x1.double() + 2 * x2.double())).reshape(B, n_dst)
+    assert torch.allclose(y12, y1 + 2 * y2, rtol=1e-11, atol=1e-9)
+    # mean preservation: area-weighted mean of a conservative remap equals that of the source
+    x1[7] = float("nan")
+    y1n = rg.regrid(x1).reshape(B, n_dst)
+    assert torch.isnan(y1n[7]).all() and not torch.isnan(y1n[6]).any()
+    rg.weights_matrix.set_kernel("gather")
+    yg = rg.regrid(x1).reshape(B, n_dst)
+    rg.weights_matrix.set_kernel(None)
+    assert torch.equal(torch.isnan(yg), torch.isnan(y1n))
+    ok = ~torch.isnan(yg)
+    assert torch.allclose(yg[ok], y1n[ok], rtol=1e-12, atol=0)
+
+
+def test_errors(smm_lib, cuda):
+    from smmregrid_b200 import Regridder, synth
+    w = synth.config_weights("C1")
+    with pytest.raises(ValueError):
+        Regridder(weights=w, remap_area_min=1.5)
+    with pytest.raises(ValueError):
+        Regridder()
+    rg = Regridder(weights=w)
+    with pytest.raises(KeyError):
+        rg.regrid(np.zeros((3, 17), np.float32))
+    with pytest.raises(TypeError):
+        rg.regrid("not an array")
+    bad = w.assign(src_address=w["src_address"] + 10**6)
+    with pytest.raises(ValueError):
+        Regridder(weights=bad)

@@ -1,0 +1,153 @@
+"""Host logic of the operator construction (no GPU): CSR build + staged tile plan.
+
+The plan arrays are pulled through the host-only introspection ABI and the staged kernel's
+data flow is EMULATED here in numpy (segments -> staged footprint -> per-lane links ->
+lane-group reduction); the emulation must reproduce the oracle.  This validates exactly what
+smm_create uploads to the device.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import assert_parity, random_links
+
+
+class HostPlan:
+    def __init__(self, lib, src, dst, rm, n_src, n_dst):
+        from smmregrid_b200 import _lib
+        self.lib = lib
+        src = np.ascontiguousarray(src, np.int32)
+        dst = np.ascontiguousarray(dst, np.int32)
+        rm = np.ascontiguousarray(rm, np.float64)
+        h = ctypes.c_void_p()
+        _lib.check(lib.smm_host_plan_build(n_src, n_dst, src.size, src.ctypes.data, dst.ctypes.data,
+                                           rm.ctypes.data, rm.shape[1], 1, ctypes.byref(h)))
+        inf = _lib.SmmInfo()
+        ns = ctypes.c_int64()
+        _lib.check(lib.smm_host_plan_info(h, ctypes.byref(inf), ctypes.byref(ns)))
+        self.info = inf.asdict()
+        nnz, nt, kpl = inf.nnz, inf.n_tiles, inf.links_per_lane
+        self.rowptr = np.empty(n_dst + 1, np.int32)
+        self.col = np.empty(nnz, np.int32)
+        self.val = np.empty(nnz, np.float64)
+        self.tiles = np.empty((nt, 8), np.int32)
+        self.segs = np.empty((ns.value, 4), np.uint32)
+        self.wplan = np.empty((nt, kpl, 256), np.float64)
+        self.iplan = np.empty((nt, kpl, 256), np.uint16)
+        _lib.check(lib.smm_host_plan_copy(h, self.rowptr.ctypes.data, self.col.ctypes.data, self.val.ctypes.data,
+                                          self.tiles.ctypes.data, self.segs.ctypes.data,
+                                          self.wplan.ctypes.data, self.iplan.ctypes.data))
+        lib.smm_host_plan_free(h)
+
+    def emulate(self, x):
+        """What staged_kernel computes for filled input x [B, n_src] (float64 math)."""
+        B = x.shape[0]
+        lpr = self.info["lanes_per_row"]
+        y = np.zeros((B, self.info["n_dst"]))
+        for t, (row0, nrows, seg0, nseg, elems, *_r) in enumerate(self.tiles):
+            stage = np.zeros((B, max(elems, 1)))
+            for s, d, ln, _p in self.segs[seg0:seg0 + nseg]:
+                stage[:, d:d + ln] = x[:, s:s + ln]
+            lane = (stage[:, self.iplan[t]] * self.wplan[t][None]).sum(axis=1)      # [B, 256]
+            rows = lane.reshape(B, 256 // lpr, lpr).sum(axis=2)
+            y[:, row0:row0 + nrows] = rows[:, :nrows]
+        return y
+
+
+def _check_plan_invariants(p, n_src):
+    t, s = p.tiles, p.segs
+    assert (t[:, 1] > 0).all() and t[:, 1].sum() == p.info["n_dst"]
+    assert (np.diff(t[:, 0]) == t[:-1, 1]).all()
+    for row0, nrows, seg0, nseg, elems, *_ in t:
+        sg = s[seg0:seg0 + nseg]
+        if nseg:
+            assert (sg[:, 0] % 8 == 0).all() and (sg[:, 1] % 8 == 0).all()      # 16-byte aligned TMA
+            assert (sg[:, 0] + sg[:, 2] <= n_src).all()
+            assert (np.diff(sg[:, 0].astype(np.int64)) > 0).all()
+            assert sg[:, 2].sum() == elems
+            assert (sg[1:, 1] == np.cumsum(sg[:-1, 2])).all()
+    assert p.iplan.max(initial=0) < max(1, p.info["max_tile_elems"])
+
+
+@pytest.mark.parametrize("nnz_per_row", [1, 2, 5, 10, 20, 50, 100, 240])
+def test_plan_emulation_matches_oracle(smm_lib, oracle, nnz_per_row):
+    rng = np.random.default_rng(nnz_per_row)
+    n_src, n_dst, B = 3000, 611, 5
+    counts = rng.integers(0, nnz_per_row + 1, size=n_dst)
+    counts[7] = nnz_per_row
+    dst = np.repeat(np.arange(n_dst), counts)
+    src = np.clip((dst * n_src) // n_dst + rng.integers(-200, 200, size=dst.size), 0, n_src - 1)
+    w = rng.random(dst.size)
+    o = rng.permutation(dst.size)                        # unsorted input, duplicates included
+    src, dst, w = src[o] + 1, dst[o] + 1, w[o].reshape(-1, 1)
+    p = HostPlan(smm_lib, src, dst, w, n_src, n_dst)
+    assert p.info["kernel_name"] == "staged", p.info
+    assert p.info["lanes_per_row"] * p.info["links_per_lane"] >= p.info["max_row_nnz"]
+    _check_plan_invariants(p, n_src)
+    mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
+    # CSR rows hold the oracle's links in ascending-src order with duplicates summed
+    o2 = np.lexsort((mat.src, mat.dst))
+    assert np.array_equal(p.col, mat.src[o2])
+    assert np.array_equal(np.repeat(np.arange(n_dst), np.diff(p.rowptr)), mat.dst[o2])
+    assert np.allclose(p.val, mat.w[o2], rtol=1e-15, atol=0)
+    x = rng.standard_normal((B, n_src))
+    y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False)
+    assert_parity(np.where(np.abs(y_ref) > 0, p.emulate(x), 0.0), y_ref, 1e-11)
+
+
+def test_plan_named_configs(smm_lib, oracle):
+    from smmregrid_b200 import synth
+    for cfg, scale, lanes in (("C1", 1, (1, 4)), ("C2", 4, (2, 16)), ("C4", 5, (8, 16))):
+        w = synth.config_weights(cfg, scale)
+        n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+        p = HostPlan(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+        assert p.info["kernel_name"] == "staged"
+        assert (p.info["lanes_per_row"], p.info["links_per_lane"]) == lanes
+        assert p.info["touched_src"] == n_src
+        if cfg != "C1":                                      # down-sampling: little over-read of the slab
+            assert p.info["sum_tile_elems"] < 1.1 * n_src
+        _check_plan_invariants(p, n_src)
+        x = np.random.default_rng(1).standard_normal((2, n_src)) + 10
+        mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+        assert_parity(p.emulate(x), oracle.apply_weights_c(x, mat, None, None, 0.0, False), 1e-12, cfg)
+
+
+def test_scattered_sources_use_gather(smm_lib):
+    from smmregrid_b200 import synth
+    w = synth.config_weights("C5dis", 8)
+    p = HostPlan(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"],
+                 w.sizes["src_grid_size"], w.sizes["dst_grid_size"])
+    assert p.info["kernel_name"] == "gather"
+    assert p.info["nnz"] == 4 * w.sizes["dst_grid_size"]
+
+
+def test_long_rows_use_gather(smm_lib):
+    n_src, n_dst = 2000, 3
+    dst = np.repeat(np.arange(n_dst), 600)
+    src = np.tile(np.arange(600), n_dst)
+    p = HostPlan(smm_lib, src + 1, dst + 1, np.ones((dst.size, 1)), n_src, n_dst)
+    assert p.info["kernel_name"] == "gather" and p.info["max_row_nnz"] == 600
+
+
+def test_empty_and_ragged(smm_lib, oracle):
+    # no links at all
+    p = HostPlan(smm_lib, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros((0, 1)), 10, 4)
+    assert p.info["nnz"] == 0 and np.array_equal(p.rowptr, np.zeros(5))
+    # one link, last cell of both grids (tail clipping of the aligned segment)
+    p = HostPlan(smm_lib, np.array([13]), np.array([4]), np.array([[2.0]]), 13, 4)
+    assert p.info["nnz"] == 1 and p.col[0] == 12
+    _check_plan_invariants(p, 13)
+    x = np.arange(13.0).reshape(1, 13)
+    assert p.emulate(x)[0, 3] == 24.0
+
+
+def test_address_range_errors(smm_lib):
+    from smmregrid_b200 import _lib
+    h = ctypes.c_void_p()
+    for src, dst in (([0], [1]), ([1], [0]), ([11], [1]), ([1], [5])):
+        s, d = np.array(src, np.int32), np.array(dst, np.int32)
+        w = np.ones((1, 1))
+        rc = smm_lib.smm_host_plan_build(10, 4, 1, s.ctypes.data, d.ctypes.data, w.ctypes.data, 1, 1, ctypes.byref(h))
+        assert rc == _lib.SMM_ERR_RANGE
+        assert b"outside the grids" in smm_lib.smm_last_error()
