@@ -151,6 +151,15 @@ def test_threshold_replay_is_reference_order(smm_lib, oracle, cuda):
     mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
     y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False)
     assert 0 < np.isnan(y_ref).sum() < y_ref.size
+    # the case is discriminating: a lane-split + tree summation of the same terms (what the
+    # fast path does) would flip hundreds of NaN decisions
+    xf = np.where(np.isfinite(x), x, 1e20)
+    o2 = np.lexsort((mat.src, mat.dst))
+    terms = xf[:, mat.src[o2].reshape(n_dst, k)] * mat.w[o2].reshape(1, n_dst, k)
+    t = sum(terms[:, :, j * 8:(j + 1) * 8] for j in range(k // 8))
+    while t.shape[-1] > 1:
+        t = t[..., ::2] + t[..., 1::2]
+    assert ((t[..., 0] > 1e19) != np.isnan(y_ref)).sum() > 50
     h = _create(smm_lib, src, dst, w, n_src, n_dst)
     try:
         for kernel in (0, 2):
