@@ -52,6 +52,8 @@ typedef struct smm_info {
     int32_t n_tiles;
     int32_t max_row_nnz;
     int32_t max_tile_segments;
+    int32_t consumer_threads;    /* staged plan: link-holding threads per CTA (256 | 512)  */
+    int32_t reserved;
     int64_t max_tile_elems;      /* largest staged source footprint of a tile (elements)  */
     int64_t sum_tile_elems;      /* sum of staged footprints: source elements one batch   */
                                  /* row pulls through TMA (>= touched columns)            */
@@ -156,7 +158,7 @@ int smm_apply_host(const smm_handle *h, int32_t level,
  * machine.  No compute entry point exists on the host side.
  *   smm_host_plan_copy: any output pointer may be NULL.  Sizes: rowptr [n_dst+1], col/val
  *   [nnz], tiles [n_tiles*8] int32 (row0,nrows,seg0,nseg,elems,pad*3), segs [n_segs*4]
- *   uint32 (src,dst,len,pad), wplan/iplan [n_tiles*links_per_lane*256].
+ *   uint32 (src,dst,len,pad), wplan/iplan [n_tiles*links_per_lane*consumer_threads].
  */
 typedef struct smm_host_plan smm_host_plan;
 int smm_host_plan_build(int64_t n_src, int64_t n_dst, int64_t nnz,

@@ -25,6 +25,7 @@ class SmmInfo(ctypes.Structure):
         ("n_src", i64), ("n_dst", i64), ("nnz", i64),
         ("n_levels", i32), ("kernel", i32), ("lanes_per_row", i32), ("links_per_lane", i32),
         ("rows_per_tile", i32), ("n_tiles", i32), ("max_row_nnz", i32), ("max_tile_segments", i32),
+        ("consumer_threads", i32), ("reserved", i32),
         ("max_tile_elems", i64), ("sum_tile_elems", i64), ("touched_src", i64), ("device_bytes", i64),
     ]
 

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -41,7 +42,7 @@ struct LevelDev {
     double *val = nullptr;
     bool staged = false;
     std::string why_not_staged;
-    int32_t lpr = 0, kpl = 0, rpt = 0, ntiles = 0, max_segs = 0;
+    int32_t lpr = 0, kpl = 0, rpt = 0, nct = 0, ntiles = 0, max_segs = 0;
     int64_t max_elems = 0, sum_elems = 0;
     TileDesc *tiles = nullptr;
     Seg *segs = nullptr;
@@ -102,7 +103,7 @@ int upload_level(const HostCsr &csr, const HostPlan &plan, LevelDev &L)
     if ((rc = upload(&L.val, csr.val, L.device_bytes))) return rc;
     L.staged = plan.ok;
     L.why_not_staged = plan.why;
-    L.lpr = plan.lpr; L.kpl = plan.kpl; L.rpt = plan.rows_per_tile;
+    L.lpr = plan.lpr; L.kpl = plan.kpl; L.rpt = plan.rows_per_tile; L.nct = plan.nct;
     if (plan.ok) {
         L.ntiles = static_cast<int32_t>(plan.tiles.size());
         L.max_segs = plan.max_tile_segments;
@@ -150,22 +151,24 @@ inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // ------------------------------------------------------------------ launch dispatch
 
 template <typename TX, typename TY>
-int launch_staged_t(int lpr, int kpl, dim3 grid, size_t smem, cudaStream_t st, const JobBatch &jb,
+int launch_staged_t(int lpr, int kpl, int nct, dim3 grid, size_t smem, cudaStream_t st, const JobBatch &jb,
                     const ApplyArgs &a)
 {
-#define SMM_CASE(L_, K_)                                                                          \
-    if (lpr == L_ && kpl == K_) {                                                                 \
-        auto kfn = staged_kernel<TX, TY, L_, K_>;                                                 \
+#define SMM_CASE_N(L_, K_, N_)                                                                    \
+    if (lpr == L_ && kpl == K_ && nct == N_) {                                                    \
+        auto kfn = staged_kernel<TX, TY, L_, K_, N_>;                                             \
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                       static_cast<int>(smem)));                                   \
-        kfn<<<grid, kStagedThreads, smem, st>>>(jb, a);                                           \
+        kfn<<<grid, N_ + 32, smem, st>>>(jb, a);                                                  \
         CUDA_TRY(cudaGetLastError());                                                             \
         g_launches.fetch_add(1, std::memory_order_relaxed);                                       \
         return SMM_OK;                                                                            \
     }
+#define SMM_CASE(L_, K_) SMM_CASE_N(L_, K_, 256) SMM_CASE_N(L_, K_, 512)
     SMM_CASE(1, 4) SMM_CASE(2, 4) SMM_CASE(1, 16) SMM_CASE(2, 16) SMM_CASE(4, 16) SMM_CASE(8, 16)
     SMM_CASE(16, 16) SMM_CASE(32, 16)
 #undef SMM_CASE
+#undef SMM_CASE_N
     return fail(SMM_ERR_INVALID, "no staged kernel for this lane configuration");
 }
 
@@ -238,6 +241,10 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
 
     ApplyArgs a{};
     a.B = B; a.x_bstride = xbs; a.y_bstride = ybs; a.remap_area_min = area_min;
+    {   // profiling aid: SMM_DEBUG_STREAM_ONLY=1 makes the staged consumers skip the arithmetic
+        const char *e = std::getenv("SMM_DEBUG_STREAM_ONLY");
+        a.debug_flags = (e && e[0] == '1') ? 1u : 0u;
+    }
 
     auto fill_job = [&](const JobSpec &s, LevelJob &j) {
         const LevelDev &L = h->levels[s.level];
@@ -253,13 +260,13 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         JobBatch jb{};
         int64_t tiles_total = 0;
         size_t max_segs = 0, max_elems = 0;
-        int lpr = 0, kpl = 0;
+        int lpr = 0, kpl = 0, nct = 256;
         for (size_t g = g0; g < g1; ++g) {
             const LevelDev &L = h->levels[staged[g].level];
             tiles_total += L.ntiles;
             max_segs = std::max<size_t>(max_segs, L.max_segs);
             max_elems = std::max<size_t>(max_elems, L.max_elems);
-            lpr = L.lpr; kpl = L.kpl;
+            lpr = L.lpr; kpl = L.kpl; nct = L.nct;
             a.n_src = L.n_src; a.n_dst = L.n_dst;
         }
         int64_t chunk = 0;
@@ -268,7 +275,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         const size_t stage_off = kSmemHeader + round_up(max_segs * sizeof(Seg), 128);
         const size_t stage_bytes = std::max<size_t>(128, round_up(max_elems * sx, 128));
         const size_t half = (228u * 1024u - 2u * 1024u) / 2u - 1024u;   // two CTAs per SM
-        size_t S = half > stage_off ? (half - stage_off) / stage_bytes : 0;
+        size_t S = (nct == 256 && half > stage_off) ? (half - stage_off) / stage_bytes : 0;
         if (S < 3) S = (h->smem_optin - stage_off) / stage_bytes;        // one CTA per SM
         S = std::min<size_t>(S, kMaxStages);
         if (S < 2) return fail(SMM_ERR_INVALID, "internal: staged footprint does not fit");
@@ -288,7 +295,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         if (item > INT32_MAX) return fail(SMM_ERR_INVALID, "too many work items in one launch");
         if (item == 0) continue;
         const dim3 grid(static_cast<unsigned>(item));
-        const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, lpr, kpl, grid, smem, st, jb, a);
+        const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, lpr, kpl, nct, grid, smem, st, jb, a);
         if (rc) return rc;
     }
 
@@ -393,10 +400,11 @@ int smm_create_levels(int32_t n_levels, const int64_t *link_length, int64_t nl_m
     // one lane configuration for every level so a grouped launch runs a single kernel
     int32_t lpr = 0, kpl = 0;
     const bool cfg = choose_lanes(max_row, lpr, kpl);
+    const int32_t nct = default_consumer_threads();
     h->levels.resize(static_cast<size_t>(n_levels));
     for (int32_t i = 0; i < n_levels; ++i) {
         HostPlan plan;
-        if (cfg) build_plan(csrs[i], lpr, kpl, plan);
+        if (cfg) build_plan(csrs[i], lpr, kpl, nct, plan);
         else plan.why = "a destination row has more than 512 links";
         rc = upload_level(csrs[i], plan, h->levels[i]);
         if (rc) { smm_destroy(h); return rc; }
@@ -435,6 +443,7 @@ int smm_get_info(const smm_handle *h, int32_t level, smm_info *out)
     out->lanes_per_row = L.lpr; out->links_per_lane = L.kpl; out->rows_per_tile = L.rpt;
     out->n_tiles = L.ntiles; out->max_row_nnz = L.max_row_nnz;
     out->max_tile_segments = L.max_segs; out->max_tile_elems = L.max_elems;
+    out->consumer_threads = L.nct;
     out->sum_tile_elems = L.sum_elems; out->touched_src = L.touched;
     out->device_bytes = L.device_bytes;
     return SMM_OK;
@@ -618,7 +627,7 @@ int smm_host_plan_build(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t
     int rc = build_csr(n_src, n_dst, nnz, src_address, dst_address, remap_matrix, num_wgts,
                        index_base, p->csr, err);
     if (rc) { delete p; return fail(rc, err); }
-    build_plan(p->csr, 0, 0, p->plan);
+    build_plan(p->csr, 0, 0, default_consumer_threads(), p->plan);
     *out = p;
     return SMM_OK;
 }
@@ -636,6 +645,7 @@ int smm_host_plan_info(const smm_host_plan *p, smm_info *out, int64_t *n_segs_ou
     out->n_tiles = p->plan.ok ? static_cast<int32_t>(p->plan.tiles.size()) : 0;
     out->max_row_nnz = p->csr.max_row_nnz;
     out->max_tile_segments = p->plan.max_tile_segments;
+    out->consumer_threads = p->plan.nct;
     out->max_tile_elems = p->plan.max_tile_elems;
     out->sum_tile_elems = p->plan.sum_tile_elems;
     out->touched_src = p->csr.touched_src;

@@ -10,9 +10,10 @@
 
 namespace smm {
 
-constexpr int kConsumerThreads = 256;               // threads holding links in registers
-constexpr int kConsumerWarps = kConsumerThreads / 32;
-constexpr int kStagedThreads = kConsumerThreads + 32;  // + one TMA producer warp
+// Consumer threads per CTA (threads holding links in registers) are a plan parameter:
+// 256 (two CTAs per SM) or 512 (one CTA per SM, tiles twice as long -> longer TMA segments).
+// The CTA adds one TMA producer warp.
+constexpr int kMaxConsumerThreads = 512;
 constexpr int kMaxStages = 12;
 constexpr int kSegAlign = 8;                        // segment bounds: multiples of 8 elements
 constexpr int kSegGap = 32;                         // merge segments closer than this
@@ -41,8 +42,8 @@ struct TileDesc {
 struct LevelJob {
     const TileDesc *tiles;
     const Seg *segs;
-    const double *wplan;      // [ntiles][KPL][256] register image of the link weights
-    const uint16_t *iplan;    // [ntiles][KPL][256] footprint-local element index per link
+    const double *wplan;      // [ntiles][KPL][NCT] register image of the link weights
+    const uint16_t *iplan;    // [ntiles][KPL][NCT] footprint-local element index per link
     const int32_t *rowptr;    // CSR by destination row, columns ascending (reference order)
     const int32_t *col;
     const double *val;
@@ -73,6 +74,8 @@ struct ApplyArgs {
     uint32_t stage_bytes; // bytes reserved per stage (>= largest footprint, 128-aligned)
     uint32_t stage_off;   // byte offset of stage 0 in dynamic shared memory
     double remap_area_min;
+    uint32_t debug_flags; // bit 0: stream only (profiling aid: consumers skip the arithmetic)
+    uint32_t pad;
 };
 
 }  // namespace smm

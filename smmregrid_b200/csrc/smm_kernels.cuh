@@ -125,10 +125,56 @@ __device__ __forceinline__ const LevelJob &find_job(const JobBatch &jb, int item
 
 // ------------------------------------------------------------------ staged kernel
 
-template <typename TX, typename TY, int LPR, int KPL>
-__global__ void __launch_bounds__(kStagedThreads, 2)
+template <typename TX> __device__ __forceinline__ TX lds(uint32_t addr);
+template <> __device__ __forceinline__ float lds<float>(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+template <> __device__ __forceinline__ double lds<double>(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// Sum of one lane's register-resident links against the staged footprint at shared address
+// `sb`.  kFill = false is the fast path: raw values, no non-finite test (any NaN/inf input
+// makes the sum non-finite, which the caller detects and redoes with kFill = true).
+template <typename TX, int KPL, bool kFill>
+__device__ __forceinline__ double lane_sum(uint32_t sb, const uint32_t (&off)[KPL], const double (&w)[KPL])
+{
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < KPL; k += 4) {
+        TX v0 = lds<TX>(sb + off[k + 0]);
+        TX v1 = lds<TX>(sb + off[k + 1]);
+        TX v2 = lds<TX>(sb + off[k + 2]);
+        TX v3 = lds<TX>(sb + off[k + 3]);
+        if (kFill) { v0 = fill_invalid(v0); v1 = fill_invalid(v1); v2 = fill_invalid(v2); v3 = fill_invalid(v3); }
+        acc0 = fma(static_cast<double>(v0), w[k + 0], acc0);
+        acc1 = fma(static_cast<double>(v1), w[k + 1], acc1);
+        acc2 = fma(static_cast<double>(v2), w[k + 2], acc2);
+        acc3 = fma(static_cast<double>(v3), w[k + 3], acc3);
+    }
+    return (acc0 + acc1) + (acc2 + acc3);
+}
+
+template <int LPR>
+__device__ __forceinline__ double group_sum(double acc)
+{
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+
+template <typename TX, typename TY, int LPR, int KPL, int NCT>
+__global__ void __launch_bounds__(NCT + 32, NCT == 256 ? 2 : 1)
 staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ ApplyArgs a)
 {
+    constexpr int kThreads = NCT + 32;
+    constexpr int kConsumerWarps = NCT / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -146,14 +192,15 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
     uint64_t *full = reinterpret_cast<uint64_t *>(smem);
     uint64_t *empty = full + kMaxStages;
     Seg *ssegs = reinterpret_cast<Seg *>(smem + kSmemHeader);
-    unsigned char *stages = smem + a.stage_off;
+    const uint32_t stages_addr = smem_u32(smem) + a.stage_off;
+    const uint32_t full_addr = smem_u32(full), empty_addr = smem_u32(empty);
     const int S = a.nstages;
 
-    for (int i = tid; i < td.nseg; i += kStagedThreads) ssegs[i] = job.segs[td.seg0 + i];
+    for (int i = tid; i < td.nseg; i += kThreads) ssegs[i] = job.segs[td.seg0 + i];
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(smem_u32(&full[s]), 1);
-            mbar_init(smem_u32(&empty[s]), kConsumerWarps);
+            mbar_init(full_addr + 8 * s, 1);
+            mbar_init(empty_addr + 8 * s, kConsumerWarps);
         }
         mbar_fence_init();
     }
@@ -167,12 +214,12 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         int s = 0;
         uint32_t ph = 0;
         for (int64_t b = b0; b < b1; ++b) {
-            mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
-            const uint32_t fb = smem_u32(&full[s]);
+            mbar_wait(empty_addr + 8 * s, ph ^ 1u);
+            const uint32_t fb = full_addr + 8 * s;
             if (lane == 0) mbar_arrive_expect_tx(fb, tile_bytes);
             __syncwarp();
             const TX *xrow = xbase + b * a.x_bstride;
-            const uint32_t sbase = smem_u32(stages + static_cast<size_t>(s) * a.stage_bytes);
+            const uint32_t sbase = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
             for (int i = lane; i < td.nseg; i += 32) {
                 const Seg sg = ssegs[i];
                 tma_bulk_g2s(sbase + sg.dst * static_cast<uint32_t>(sizeof(TX)), xrow + sg.src,
@@ -190,11 +237,11 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         double w[KPL];
         uint32_t off[KPL];
         {
-            const size_t base = static_cast<size_t>(tile) * KPL * kConsumerThreads + tid;
+            const size_t base = static_cast<size_t>(tile) * KPL * NCT + tid;
 #pragma unroll
             for (int k = 0; k < KPL; ++k) {
-                w[k] = __ldg(job.wplan + base + static_cast<size_t>(k) * kConsumerThreads);
-                off[k] = static_cast<uint32_t>(__ldg(job.iplan + base + static_cast<size_t>(k) * kConsumerThreads)) *
+                w[k] = __ldg(job.wplan + base + static_cast<size_t>(k) * NCT);
+                off[k] = static_cast<uint32_t>(__ldg(job.iplan + base + static_cast<size_t>(k) * NCT)) *
                          static_cast<uint32_t>(sizeof(TX));
             }
         }
@@ -205,29 +252,23 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         }
         TY *yrow = static_cast<TY *>(job.y) + row;
         const TX *xbase = static_cast<const TX *>(job.x);
+        const bool stream_only = (a.debug_flags & 1u) != 0;
 
         int s = 0;
         uint32_t ph = 0;
         for (int64_t b = b0; b < b1; ++b) {
-            mbar_wait(smem_u32(&full[s]), ph);
-            const unsigned char *st = stages + static_cast<size_t>(s) * a.stage_bytes;
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll
-            for (int k = 0; k < KPL; k += 4) {
-                const TX v0 = fill_invalid(*reinterpret_cast<const TX *>(st + off[k + 0]));
-                const TX v1 = fill_invalid(*reinterpret_cast<const TX *>(st + off[k + 1]));
-                const TX v2 = fill_invalid(*reinterpret_cast<const TX *>(st + off[k + 2]));
-                const TX v3 = fill_invalid(*reinterpret_cast<const TX *>(st + off[k + 3]));
-                acc0 = fma(static_cast<double>(v0), w[k + 0], acc0);
-                acc1 = fma(static_cast<double>(v1), w[k + 1], acc1);
-                acc2 = fma(static_cast<double>(v2), w[k + 2], acc2);
-                acc3 = fma(static_cast<double>(v3), w[k + 3], acc3);
+            mbar_wait(full_addr + 8 * s, ph);
+            const uint32_t sb = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
+            double acc = 0.0;
+            if (!stream_only) {
+                acc = group_sum<LPR>(lane_sum<TX, KPL, false>(sb, off, w));
+                // a non-finite sum means some source value was NaN/inf (regrid.py:545-547 fills
+                // them with 1e20): redo the warp's rows with the fill applied
+                if (__any_sync(0xffffffffu, !(fabs(acc) <= 1.7976931348623157e+308)))
+                    acc = group_sum<LPR>(lane_sum<TX, KPL, true>(sb, off, w));
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&empty[s]));   // stage may be refilled
-            double acc = (acc0 + acc1) + (acc2 + acc3);
-#pragma unroll
-            for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) mbar_arrive(empty_addr + 8 * s);   // stage may be refilled
             if (l_in == 0 && valid) {
                 if (near_threshold(acc))
                     acc = replay_row<TX>(job.rowptr, job.col, job.val, row, xbase + b * a.x_bstride);

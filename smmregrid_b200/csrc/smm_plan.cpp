@@ -8,6 +8,7 @@
 #include "smm_plan.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 
 #include "../../include/smmregrid_b200.h"
@@ -99,9 +100,20 @@ bool choose_lanes(int32_t m, int32_t &lpr, int32_t &kpl)
     return true;
 }
 
-void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, HostPlan &plan)
+int32_t default_consumer_threads()
+{
+    const char *e = std::getenv("SMM_CONSUMER_THREADS");
+    if (e) {
+        const int v = std::atoi(e);
+        if (v == 256 || v == 512) return v;
+    }
+    return 256;
+}
+
+void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, HostPlan &plan)
 {
     plan = HostPlan{};
+    if (nct != 256 && nct != 512) nct = 256;
     int32_t lpr = force_lpr, kpl = force_kpl;
     if (lpr <= 0 || kpl <= 0) {
         if (!choose_lanes(csr.max_row_nnz, lpr, kpl)) {
@@ -113,13 +125,13 @@ void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, HostPl
         return;
     }
     const int64_t n_dst = csr.n_dst, n_src = csr.n_src;
-    const int32_t R = kConsumerThreads / lpr;
+    const int32_t R = nct / lpr;
     const int64_t ntiles = (n_dst + R - 1) / R;
     if (ntiles > INT32_MAX / 2) { plan.why = "too many tiles"; return; }
-    plan.lpr = lpr; plan.kpl = kpl; plan.rows_per_tile = R;
+    plan.lpr = lpr; plan.kpl = kpl; plan.rows_per_tile = R; plan.nct = nct;
     plan.tiles.resize(static_cast<size_t>(ntiles));
-    plan.wplan.assign(static_cast<size_t>(ntiles) * kpl * kConsumerThreads, 0.0);
-    plan.iplan.assign(static_cast<size_t>(ntiles) * kpl * kConsumerThreads, 0);
+    plan.wplan.assign(static_cast<size_t>(ntiles) * kpl * nct, 0.0);
+    plan.iplan.assign(static_cast<size_t>(ntiles) * kpl * nct, 0);
 
     std::vector<int32_t> cols;
     int64_t sum_blocks = 0;    // distinct aligned 8-element blocks touched, summed over tiles
@@ -164,27 +176,127 @@ void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, HostPl
         plan.sum_tile_elems += off;
         if (off > 65535u) { plan.why = "tile footprint exceeds 16-bit local indices"; return; }
 
-        // register image: link e of a row -> lane (e % lpr) of the row's lane group, slot e / lpr
+        // Register image.  A row's links may sit in any (lane, slot) of the row's lane group --
+        // the kernel sums them all -- so the assignment is chosen to spread each warp-wide
+        // shared-memory load over distinct banks: per warp and per slot, a bipartite matching
+        // of lanes to banks (4-byte elements: bank = local index % 32) over the links each
+        // lane's row still has to place.  Unplaced slots carry weight 0 and re-read the row's
+        // first link (the fast path skips the non-finite test, so a padded slot must never see
+        // a NaN the row does not own).
         const Seg *sb = plan.segs.data() + td.seg0;
-        const size_t tbase = static_cast<size_t>(t) * kpl * kConsumerThreads;
-        for (int64_t r = r0; r < r1; ++r) {
-            const int32_t a = csr.rowptr[r], b = csr.rowptr[r + 1];
-            for (int32_t j = a; j < b; ++j) {
-                const uint32_t c = static_cast<uint32_t>(csr.col[j]);
-                // last segment with src <= c
-                int lo = 0, hi = td.nseg - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (sb[mid].src <= c) lo = mid; else hi = mid - 1;
+        const size_t tbase = static_cast<size_t>(t) * kpl * nct;
+        const int rows_per_warp = 32 / lpr;
+        const int nwarps = nct / 32;
+        struct Link { uint16_t li; double w; };
+        std::vector<std::vector<Link>> bucket(static_cast<size_t>(rows_per_warp) * 32);
+        for (int wi = 0; wi < nwarps; ++wi) {
+            uint16_t first_li[32] = {0};
+            int remaining[32] = {0};
+            int32_t rep[32][32];                         // one link of the row per bank, for padding
+            for (auto &rr : rep) for (int32_t &v : rr) v = -1;
+            for (auto &b : bucket) b.clear();
+            for (int jr = 0; jr < rows_per_warp; ++jr) {
+                const int64_t r = r0 + static_cast<int64_t>(wi) * rows_per_warp + jr;
+                if (r >= r1) continue;
+                const int32_t a = csr.rowptr[r], b = csr.rowptr[r + 1];
+                for (int32_t j = b - 1; j >= a; --j) {          // pushed in reverse: popped ascending
+                    const uint32_t c = static_cast<uint32_t>(csr.col[j]);
+                    int lo = 0, hi = td.nseg - 1;                 // last segment with src <= c
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (sb[mid].src <= c) lo = mid; else hi = mid - 1;
+                    }
+                    const uint32_t li = sb[lo].dst + (c - sb[lo].src);
+                    bucket[static_cast<size_t>(jr) * 32 + (li & 31u)].push_back(Link{static_cast<uint16_t>(li), csr.val[j]});
+                    rep[jr][li & 31u] = static_cast<int32_t>(li);
+                    if (j == a) first_li[jr] = static_cast<uint16_t>(li);
                 }
-                const uint32_t li = sb[lo].dst + (c - sb[lo].src);
-                const int32_t e = j - a;
-                const int32_t thread = static_cast<int32_t>(r - r0) * lpr + (e % lpr);
-                const int32_t slot = e / lpr;
-                plan.wplan[tbase + static_cast<size_t>(slot) * kConsumerThreads + thread] = csr.val[j];
-                plan.iplan[tbase + static_cast<size_t>(slot) * kConsumerThreads + thread] =
-                    static_cast<uint16_t>(li);
+                remaining[jr] = b - a;
             }
+            for (int k = 0; k < kpl; ++k) {
+                uint32_t cand[32];
+                int order[32], ncand[32];
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int jr = lane / lpr;
+                    uint32_t m = 0;
+                    for (int b = 0; b < 32; ++b)
+                        if (!bucket[static_cast<size_t>(jr) * 32 + b].empty()) m |= 1u << b;
+                    cand[lane] = m;
+                    ncand[lane] = __builtin_popcount(m);
+                    order[lane] = lane;
+                }
+                std::stable_sort(order, order + 32, [&](int x, int y) { return ncand[x] < ncand[y]; });
+                int owner[32];
+                int lane_bank[32];
+                for (int b = 0; b < 32; ++b) { owner[b] = -1; lane_bank[b] = -1; }
+                // a lane may only be matched while its row still has links left for this slot:
+                // a row with fewer remaining links than lanes matches only that many lanes
+                int quota[32];
+                for (int jr = 0; jr < rows_per_warp; ++jr) quota[jr] = remaining[jr];
+                auto augment = [&](auto &&self, int lane, uint32_t &seen) -> bool {
+                    uint32_t m = cand[lane] & ~seen;
+                    while (m) {
+                        const int b = __builtin_ctz(m);
+                        m &= m - 1;
+                        seen |= 1u << b;
+                        if (owner[b] < 0 || self(self, owner[b], seen)) { owner[b] = lane; return true; }
+                    }
+                    return false;
+                };
+                bool matched[32] = {false};
+                for (int oi = 0; oi < 32; ++oi) {
+                    const int lane = order[oi];
+                    const int jr = lane / lpr;
+                    if (quota[jr] <= 0 || cand[lane] == 0) continue;
+                    uint32_t seen = 0;
+                    if (augment(augment, lane, seen)) { matched[lane] = true; --quota[jr]; }
+                }
+                for (int b = 0; b < 32; ++b) if (owner[b] >= 0) lane_bank[owner[b]] = b;
+                // a bucket holds links of one bank: two lanes of a row matched to the same row's
+                // buckets always differ in bank, so each pops its own link
+                int load[32] = {0};
+                Link chosen[32];
+                bool have[32] = {false};
+                for (int lane = 0; lane < 32; ++lane) {
+                    if (!matched[lane] || lane_bank[lane] < 0) continue;
+                    const int jr = lane / lpr;
+                    auto &bk = bucket[static_cast<size_t>(jr) * 32 + lane_bank[lane]];
+                    if (bk.empty()) continue;            // bank taken by a same-row lane in a previous augmentation
+                    chosen[lane] = bk.back(); bk.pop_back(); have[lane] = true;
+                    --remaining[jr]; ++load[lane_bank[lane]];
+                }
+                for (int lane = 0; lane < 32; ++lane) {
+                    if (have[lane]) continue;
+                    const int jr = lane / lpr;
+                    if (remaining[jr] <= 0) continue;
+                    int best = -1;
+                    for (int b = 0; b < 32; ++b)
+                        if (!bucket[static_cast<size_t>(jr) * 32 + b].empty() && (best < 0 || load[b] < load[best])) best = b;
+                    auto &bk = bucket[static_cast<size_t>(jr) * 32 + best];
+                    chosen[lane] = bk.back(); bk.pop_back(); have[lane] = true;
+                    --remaining[jr]; ++load[best];
+                }
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int thread = wi * 32 + lane;
+                    const size_t at = tbase + static_cast<size_t>(k) * nct + thread;
+                    if (have[lane]) {
+                        plan.wplan[at] = chosen[lane].w;
+                        plan.iplan[at] = chosen[lane].li;
+                    } else {
+                        // padding: weight 0 on one of the row's own links, in a bank this slot
+                        // does not use yet when the row has one there
+                        const int jr = lane / lpr;
+                        int pick = -1;
+                        for (int b = 0; b < 32 && pick < 0; ++b)
+                            if (load[b] == 0 && rep[jr][b] >= 0) pick = b;
+                        plan.wplan[at] = 0.0;
+                        if (pick >= 0) { plan.iplan[at] = static_cast<uint16_t>(rep[jr][pick]); ++load[pick]; }
+                        else plan.iplan[at] = first_li[jr];
+                    }
+                }
+            }
+            for (int jr = 0; jr < rows_per_warp; ++jr)
+                if (remaining[jr] != 0) { plan.why = "internal: link placement failed"; return; }
         }
     }
     // Staging pays when footprints are compact runs; otherwise the gather kernel is used.

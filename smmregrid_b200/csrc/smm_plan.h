@@ -29,10 +29,11 @@ struct HostPlan {
     bool ok = false;          // false: level is served by the gather kernel only
     std::string why;          // reason when !ok
     int32_t lpr = 0, kpl = 0, rows_per_tile = 0;
+    int32_t nct = 0;          // consumer threads per CTA the register image is laid out for
     std::vector<TileDesc> tiles;
     std::vector<Seg> segs;
-    std::vector<double> wplan;     // [ntiles][kpl][256]
-    std::vector<uint16_t> iplan;   // [ntiles][kpl][256]
+    std::vector<double> wplan;     // [ntiles][kpl][nct]
+    std::vector<uint16_t> iplan;   // [ntiles][kpl][nct]
     int32_t max_tile_segments = 0;
     int64_t max_tile_elems = 0;
     int64_t sum_tile_elems = 0;
@@ -43,6 +44,10 @@ struct HostPlan {
 bool choose_lanes(int32_t max_row_nnz, int32_t &lpr, int32_t &kpl);
 
 // force_lpr/force_kpl > 0 impose a configuration shared by all levels of a 3-D weight set.
-void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, HostPlan &plan);
+// nct = consumer threads per CTA (256 or 512).
+void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, HostPlan &plan);
+
+// Consumer threads per CTA for a weight set: SMM_CONSUMER_THREADS=256|512 overrides the default.
+int32_t default_consumer_threads();
 
 }  // namespace smm

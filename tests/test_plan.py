@@ -28,13 +28,14 @@ class HostPlan:
         _lib.check(lib.smm_host_plan_info(h, ctypes.byref(inf), ctypes.byref(ns)))
         self.info = inf.asdict()
         nnz, nt, kpl = inf.nnz, inf.n_tiles, inf.links_per_lane
+        self.nct = nct = inf.consumer_threads or 256
         self.rowptr = np.empty(n_dst + 1, np.int32)
         self.col = np.empty(nnz, np.int32)
         self.val = np.empty(nnz, np.float64)
         self.tiles = np.empty((nt, 8), np.int32)
         self.segs = np.empty((ns.value, 4), np.uint32)
-        self.wplan = np.empty((nt, kpl, 256), np.float64)
-        self.iplan = np.empty((nt, kpl, 256), np.uint16)
+        self.wplan = np.empty((nt, kpl, nct), np.float64)
+        self.iplan = np.empty((nt, kpl, nct), np.uint16)
         _lib.check(lib.smm_host_plan_copy(h, self.rowptr.ctypes.data, self.col.ctypes.data, self.val.ctypes.data,
                                           self.tiles.ctypes.data, self.segs.ctypes.data,
                                           self.wplan.ctypes.data, self.iplan.ctypes.data))
@@ -49,8 +50,8 @@ class HostPlan:
             stage = np.zeros((B, max(elems, 1)))
             for s, d, ln, _p in self.segs[seg0:seg0 + nseg]:
                 stage[:, d:d + ln] = x[:, s:s + ln]
-            lane = (stage[:, self.iplan[t]] * self.wplan[t][None]).sum(axis=1)      # [B, 256]
-            rows = lane.reshape(B, 256 // lpr, lpr).sum(axis=2)
+            lane = (stage[:, self.iplan[t]] * self.wplan[t][None]).sum(axis=1)      # [B, nct]
+            rows = lane.reshape(B, self.nct // lpr, lpr).sum(axis=2)
             y[:, row0:row0 + nrows] = rows[:, :nrows]
         return y
 
