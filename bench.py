@@ -60,6 +60,10 @@ def workload(name):
     if name.startswith("C4s"):
         k = int(name[3:])
         return synth.config_weights("C4", k), 64, f"C4 scaled 1/{k}: {3600 // k}x{1800 // k} -> {360 // k}x{180 // k} remapcon"
+    if name.startswith("con:"):          # con:<nlon_s>x<nlat_s>:<nlon_d>x<nlat_d>  (experiments)
+        _, a, b = name.split(":")
+        (ls, ts), (ld, td) = [tuple(int(v) for v in g.split("x")) for g in (a, b)]
+        return synth.conservative_latlon(ls, ts, ld, td), 1024, f"remapcon {ls}x{ts} -> {ld}x{td}"
     raise SystemExit(f"unknown workload {name}")
 
 

@@ -159,7 +159,7 @@ int launch_staged_t(int lpr, int kpl, int nct, dim3 grid, size_t smem, cudaStrea
         auto kfn = staged_kernel<TX, TY, L_, K_, N_>;                                             \
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                       static_cast<int>(smem)));                                   \
-        kfn<<<grid, N_ + 32, smem, st>>>(jb, a);                                                  \
+        kfn<<<grid, N_ + 32 * kProducerWarps, smem, st>>>(jb, a);                                 \
         CUDA_TRY(cudaGetLastError());                                                             \
         g_launches.fetch_add(1, std::memory_order_relaxed);                                       \
         return SMM_OK;                                                                            \
@@ -170,6 +170,12 @@ int launch_staged_t(int lpr, int kpl, int nct, dim3 grid, size_t smem, cudaStrea
 #undef SMM_CASE
 #undef SMM_CASE_N
     return fail(SMM_ERR_INVALID, "no staged kernel for this lane configuration");
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
 }
 
 template <typename TX, typename TY>
@@ -278,6 +284,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         size_t S = (nct == 256 && half > stage_off) ? (half - stage_off) / stage_bytes : 0;
         if (S < 3) S = (h->smem_optin - stage_off) / stage_bytes;        // one CTA per SM
         S = std::min<size_t>(S, kMaxStages);
+        S = std::min<size_t>(S, static_cast<size_t>(std::max(2, env_int("SMM_MAX_STAGES", kMaxStages))));
         if (S < 2) return fail(SMM_ERR_INVALID, "internal: staged footprint does not fit");
         a.nstages = static_cast<int32_t>(S);
         a.stage_bytes = static_cast<uint32_t>(stage_bytes);

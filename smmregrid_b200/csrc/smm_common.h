@@ -12,12 +12,12 @@ namespace smm {
 
 // Consumer threads per CTA (threads holding links in registers) are a plan parameter:
 // 256 (two CTAs per SM) or 512 (one CTA per SM, tiles twice as long -> longer TMA segments).
-// The CTA adds one TMA producer warp.
+// The CTA adds a warpgroup of four TMA producer warps.
 constexpr int kMaxConsumerThreads = 512;
 constexpr int kMaxStages = 12;
 constexpr int kSegAlign = 8;                        // segment bounds: multiples of 8 elements
 constexpr int kSegGap = 32;                         // merge segments closer than this
-constexpr int kSmemHeader = 256;                    // full[] + empty[] mbarriers
+constexpr int kSmemHeader = 256;                    // full[12] + empty[12] mbarriers
 constexpr int kMaxJobs = 24;                        // levels per grouped launch (by-value args)
 constexpr int kGatherThreads = 256;
 constexpr int kGatherBT = 4;                        // batch rows register-blocked by the gather kernel
@@ -75,7 +75,6 @@ struct ApplyArgs {
     uint32_t stage_off;   // byte offset of stage 0 in dynamic shared memory
     double remap_area_min;
     uint32_t debug_flags; // bit 0: stream only (profiling aid: consumers skip the arithmetic)
-    uint32_t pad;
 };
 
 }  // namespace smm

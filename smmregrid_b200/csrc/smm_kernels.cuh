@@ -1,7 +1,7 @@
 // smm_kernels.cuh -- sm_100a kernels of the weight-application path.
 //
 //   staged_kernel   Y = X.W for matrices whose tiles have a compact source footprint
-//                   (structured / locally ordered sources).  One producer warp streams the
+//                   (structured / locally ordered sources).  Four producer warps stream the
 //                   tile's footprint of each batch row into shared memory with 1-D TMA bulk
 //                   copies (cp.async.bulk + mbarrier complete_tx, L2 evict-first); eight
 //                   consumer warps hold the tile's link weights and footprint offsets in
@@ -142,6 +142,25 @@ template <> __device__ __forceinline__ double lds<double>(uint32_t addr)
 // Sum of one lane's register-resident links against the staged footprint at shared address
 // `sb`.  kFill = false is the fast path: raw values, no non-finite test (any NaN/inf input
 // makes the sum non-finite, which the caller detects and redoes with kFill = true).
+template <int LPR>
+__device__ __forceinline__ double group_sum(double acc)
+{
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+
+// keeps a value in a register: stops the compiler from re-deriving the shared window base
+// (S2UR SR_CgaCtaId + shifts) in front of every mbarrier operation of the batch loop
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v)
+{
+    asm volatile("mov.b32 %0, %0;" : "+r"(v));
+    return v;
+}
+
+// Sum of one lane's register-resident links against the staged footprint at shared address
+// `sb`.  kFill = false is the fast path: raw values, no non-finite test (any NaN/inf input
+// makes the sum non-finite, which the caller detects and redoes with kFill = true).
 template <typename TX, int KPL, bool kFill>
 __device__ __forceinline__ double lane_sum(uint32_t sb, const uint32_t (&off)[KPL], const double (&w)[KPL])
 {
@@ -161,19 +180,29 @@ __device__ __forceinline__ double lane_sum(uint32_t sb, const uint32_t (&off)[KP
     return (acc0 + acc1) + (acc2 + acc3);
 }
 
-template <int LPR>
-__device__ __forceinline__ double group_sum(double acc)
-{
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    return acc;
-}
+__device__ __forceinline__ bool not_finite(double v) { return !(fabs(v) <= 1.7976931348623157e+308); }
+
+// CTA roles: NCT/32 consumer warps (two warpgroups for NCT = 256) | one warpgroup of 4 TMA
+// producer warps.
+//
+// Issuing one bulk copy costs a warp ~100 cycles of serial latency (uniform-register operand
+// moves + TMA hand-off) and a tile's footprint is 10-20 segments per batch row, so a single
+// producer warp caps the CTA well below the HBM rate (measured: 5.6 TB/s with one producer
+// warp, 6.5 TB/s with four).  The segments of a stage are therefore split over four producer
+// warps whose issue latencies overlap.
+//
+// Registers: two CTAs of 12 warps per SM = 6 warps per SM sub-partition -> 80 registers per
+// thread at launch; the producer warpgroup then shrinks to 40 and the consumer warpgroups
+// grow to 96 (setmaxnreg), which the link weights + offsets held in registers need.
+constexpr int kProducerWarps = 4;
+constexpr int kProducerRegs = 40;
+constexpr int kConsumerRegs = 96;
 
 template <typename TX, typename TY, int LPR, int KPL, int NCT>
-__global__ void __launch_bounds__(NCT + 32, NCT == 256 ? 2 : 1)
+__global__ void __launch_bounds__(NCT + 32 * kProducerWarps, NCT == 256 ? 2 : 1)
 staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ ApplyArgs a)
 {
-    constexpr int kThreads = NCT + 32;
+    constexpr int kThreads = NCT + 32 * kProducerWarps;
     constexpr int kConsumerWarps = NCT / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -189,14 +218,19 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
     const int64_t b1 = (b0 + a.chunk < a.B) ? b0 + a.chunk : a.B;
     const TileDesc td = job.tiles[tile];
 
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem);
-    uint64_t *empty = full + kMaxStages;
-    Seg *ssegs = reinterpret_cast<Seg *>(smem + kSmemHeader);
-    const uint32_t stages_addr = smem_u32(smem) + a.stage_off;
-    const uint32_t full_addr = smem_u32(full), empty_addr = smem_u32(empty);
+    // per-tile segment table in bytes: {dst offset in the stage, length, source offset in the row}
+    struct SegB { uint32_t dst, len; uint64_t src; };
+    SegB *ssegs = reinterpret_cast<SegB *>(smem + kSmemHeader);
+    const uint32_t smem_addr = pin_reg(smem_u32(smem));
+    const uint32_t full_addr = smem_addr, empty_addr = smem_addr + 8 * kMaxStages;
+    const uint32_t stages_addr = smem_addr + a.stage_off;
     const int S = a.nstages;
 
-    for (int i = tid; i < td.nseg; i += kThreads) ssegs[i] = job.segs[td.seg0 + i];
+    for (int i = tid; i < td.nseg; i += kThreads) {
+        const Seg sg = job.segs[td.seg0 + i];
+        ssegs[i] = SegB{sg.dst * static_cast<uint32_t>(sizeof(TX)), sg.len * static_cast<uint32_t>(sizeof(TX)),
+                        static_cast<uint64_t>(sg.src) * sizeof(TX)};
+    }
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(full_addr + 8 * s, 1);
@@ -206,29 +240,33 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
     }
     __syncthreads();
 
-    if (warp == kConsumerWarps) {
-        // ---------------- producer warp: TMA bulk copies of the footprint, one stage per batch row
+    if (warp >= kConsumerWarps) {
+        // ---------------- producer warps: TMA bulk copies of the footprint, one stage per batch
+        // row; producer p issues segments p, p + 4, ... (one per lane)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
+        const int p = warp - kConsumerWarps;
         const uint64_t policy = l2_evict_first_policy();
-        const TX *xbase = static_cast<const TX *>(job.x);
+        const char *xbase = static_cast<const char *>(job.x);
         const uint32_t tile_bytes = static_cast<uint32_t>(td.elems) * sizeof(TX);
         int s = 0;
         uint32_t ph = 0;
         for (int64_t b = b0; b < b1; ++b) {
             mbar_wait(empty_addr + 8 * s, ph ^ 1u);
             const uint32_t fb = full_addr + 8 * s;
-            if (lane == 0) mbar_arrive_expect_tx(fb, tile_bytes);
-            __syncwarp();
-            const TX *xrow = xbase + b * a.x_bstride;
+            // the phase cannot complete before this arrive, so copies of the other producers that
+            // land earlier only drive the transaction count transiently negative
+            if (p == 0 && lane == 0) mbar_arrive_expect_tx(fb, tile_bytes);
+            const char *xrow = xbase + b * a.x_bstride * static_cast<int64_t>(sizeof(TX));
             const uint32_t sbase = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
-            for (int i = lane; i < td.nseg; i += 32) {
-                const Seg sg = ssegs[i];
-                tma_bulk_g2s(sbase + sg.dst * static_cast<uint32_t>(sizeof(TX)), xrow + sg.src,
-                             sg.len * static_cast<uint32_t>(sizeof(TX)), fb, policy);
+            for (int i = p + kProducerWarps * lane; i < td.nseg; i += 32 * kProducerWarps) {
+                const SegB e = ssegs[i];
+                tma_bulk_g2s(sbase + e.dst, xrow + e.src, e.len, fb, policy);
             }
             if (++s == S) { s = 0; ph ^= 1u; }
         }
     } else {
         // ---------------- consumer warps: links live in registers for the whole batch loop
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
         const int r_in = tid / LPR;
         const int l_in = tid % LPR;
         const int row = td.row0 + r_in;
@@ -261,14 +299,14 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
             const uint32_t sb = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
             double acc = 0.0;
             if (!stream_only) {
-                acc = group_sum<LPR>(lane_sum<TX, KPL, false>(sb, off, w));
-                // a non-finite sum means some source value was NaN/inf (regrid.py:545-547 fills
-                // them with 1e20): redo the warp's rows with the fill applied
-                if (__any_sync(0xffffffffu, !(fabs(acc) <= 1.7976931348623157e+308)))
-                    acc = group_sum<LPR>(lane_sum<TX, KPL, true>(sb, off, w));
+                // fast path: raw values.  A non-finite partial means some source value was NaN/inf
+                // (regrid.py:545-547 fills those with 1e20): redo the warp's links with the fill.
+                acc = lane_sum<TX, KPL, false>(sb, off, w);
+                if (__any_sync(0xffffffffu, not_finite(acc))) acc = lane_sum<TX, KPL, true>(sb, off, w);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_addr + 8 * s);   // stage may be refilled
+            acc = group_sum<LPR>(acc);
             if (l_in == 0 && valid) {
                 if (near_threshold(acc))
                     acc = replay_row<TX>(job.rowptr, job.col, job.val, row, xbase + b * a.x_bstride);
