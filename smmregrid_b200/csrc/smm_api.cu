@@ -407,7 +407,7 @@ int smm_create_levels(int32_t n_levels, const int64_t *link_length, int64_t nl_m
     // one lane configuration for every level so a grouped launch runs a single kernel
     int32_t lpr = 0, kpl = 0;
     const bool cfg = choose_lanes(max_row, lpr, kpl);
-    const int32_t nct = default_consumer_threads();
+    const int32_t nct = default_consumer_threads(n_dst, lpr, h->sm_count);
     h->levels.resize(static_cast<size_t>(n_levels));
     for (int32_t i = 0; i < n_levels; ++i) {
         HostPlan plan;
@@ -634,7 +634,11 @@ int smm_host_plan_build(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t
     int rc = build_csr(n_src, n_dst, nnz, src_address, dst_address, remap_matrix, num_wgts,
                        index_base, p->csr, err);
     if (rc) { delete p; return fail(rc, err); }
-    build_plan(p->csr, 0, 0, default_consumer_threads(), p->plan);
+    {
+        int32_t lpr = 0, kpl = 0;
+        const bool cfg = choose_lanes(p->csr.max_row_nnz, lpr, kpl);
+        build_plan(p->csr, 0, 0, default_consumer_threads(n_dst, cfg ? lpr : 0, 148), p->plan);
+    }
     *out = p;
     return SMM_OK;
 }

@@ -100,14 +100,16 @@ bool choose_lanes(int32_t m, int32_t &lpr, int32_t &kpl)
     return true;
 }
 
-int32_t default_consumer_threads()
+int32_t default_consumer_threads(int64_t n_dst, int32_t lpr, int32_t sm_count)
 {
     const char *e = std::getenv("SMM_CONSUMER_THREADS");
     if (e) {
         const int v = std::atoi(e);
         if (v == 256 || v == 512) return v;
     }
-    return 256;
+    if (lpr <= 0) return 256;
+    const int64_t tiles512 = (n_dst + 512 / lpr - 1) / (512 / lpr);
+    return tiles512 >= sm_count ? 512 : 256;
 }
 
 void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, HostPlan &plan)

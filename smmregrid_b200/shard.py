@@ -1,0 +1,73 @@
+"""Batch-axis sharding over the GPUs of one box.
+
+Every batch row (time step x level x any other kept dim) is an independent product with the
+same operator (the reference contracts only ``n_src``, ``regrid.py:550``; dask splits exactly
+this axis into chunks), so ranks take contiguous blocks of the flattened batch axis, the
+operator is replicated per GPU and the hot path needs no collective.  The only communication
+is the optional final gather of the (small) destination slabs.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+
+def batch_shard(B: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block ``[start, stop)`` of ``B`` batch rows owned by ``rank``:
+    ``ceil(B / world)`` rows per rank, the last ranks possibly short or empty."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"rank {rank} outside world of {world}")
+    per = -(-B // world)
+    start = min(B, rank * per)
+    return start, min(B, start + per)
+
+
+def shard_sizes(B: int, world: int):
+    return [batch_shard(B, world, r)[1] - batch_shard(B, world, r)[0] for r in range(world)]
+
+
+def gather_to_host(y_local, B: int, group=None, dst: Optional[int] = 0):
+    """Assemble the full ``[B, ...]`` result from per-rank blocks (order = rank order).
+
+    ``y_local``: this rank's ``[b_rank, ...]`` torch tensor (CUDA with NCCL, CPU with gloo).
+    Returns a CPU tensor on rank ``dst`` (all ranks if ``dst is None``), else ``None``.
+    Blocks are padded to ``ceil(B / world)`` rows for ``all_gather_into_tensor``.
+    """
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return y_local.cpu()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    per = -(-B // world)
+    tail = tuple(y_local.shape[1:])
+    pad = torch.zeros((per,) + tail, dtype=y_local.dtype, device=y_local.device)
+    pad[: y_local.shape[0]] = y_local
+    out = torch.empty((world * per,) + tail, dtype=y_local.dtype, device=y_local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    if dst is not None and rank != dst:
+        return None
+    return out[:B].cpu()
+
+
+def regrid_sharded(regridder, x, group=None, gather: bool = True, dst: Optional[int] = 0):
+    """Regrid this rank's block of the leading (batch) axis of ``x`` and optionally gather.
+
+    ``x`` is the FULL array on every rank (or a lazily sliceable object); only
+    ``x[start:stop]`` of this rank is touched.  2-D operators only (for 3-D weights shard the
+    time axis yourself and call ``Regridder.regrid`` on the block).
+    """
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    B = x.shape[0]
+    start, stop = batch_shard(B, world, rank)
+    y_local = regridder.regrid(x[start:stop])
+    if not gather:
+        return y_local
+    import torch
+    if not isinstance(y_local, torch.Tensor):
+        y_local = torch.from_numpy(y_local)
+    return gather_to_host(y_local, B, group=group, dst=dst)
