@@ -346,6 +346,13 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     abytes = algorithmic_bytes(info, B, sx, sy, masked, area_min)
+    traffic = None            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+    try:
+        for t in json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["captures"]:
+            if (t["workload"], t["batch_rows"], t["x_dtype"], t["y_dtype"]) == (args.workload, B, args.xdtype, args.ydtype):
+                traffic = t["dram_bytes_per_launch"]
+    except Exception:
+        pass
     avg_launch_s = 1e-3 * sum(per_launch_ms) / len(per_launch_ms)
     achieved = abytes / avg_launch_s / 1e9
     value = world * B * n_src * args.steps / (total_ms_max * 1e-3)
@@ -369,7 +376,7 @@ def main():
                    "parallelism": f"batch-sharded x{world}, weights replicated, no collective",
                    "l2": "resident slab (%.1f GB) >> 126 MB L2, no flush" % (B * n_src * sx / 1e9)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": avg_launch_s * 1e3,
                      "kernel": "smm::staged_kernel" if info["kernel_name"] == "staged" else "smm::gather_kernel",
                      # stricter touched-source model: only source columns with >= 1 link

@@ -573,8 +573,10 @@ int smm_apply_host(const smm_handle *hc, int32_t level, const void *x, int32_t x
     if (ldx < L.n_src || ldy < L.n_dst) return fail(SMM_ERR_INVALID, "ldx < n_src or ldy < n_dst");
     const size_t sx = x_dtype == SMM_F32 ? 4 : 8, sy = y_dtype == SMM_F32 ? 4 : 8;
     if (chunk_rows <= 0) {
-        // ~256 MB of source per chunk, at least 32 rows when the batch allows
-        chunk_rows = std::max<int64_t>(32, (int64_t{256} << 20) / std::max<int64_t>(1, L.n_src * sx));
+        // ~256 MB of source per chunk (pipeline fill/drain of a few percent on multi-GB batches),
+        // at least 4 rows; SMM_HOST_CHUNK_MB overrides
+        const int64_t mb = std::max(1, env_int("SMM_HOST_CHUNK_MB", 256));
+        chunk_rows = std::max<int64_t>(4, (mb << 20) / std::max<int64_t>(1, L.n_src * sx));
     }
     chunk_rows = std::min(chunk_rows, B);
     std::lock_guard<std::mutex> lock(h->host_mu);
@@ -603,13 +605,19 @@ int smm_apply_host(const smm_handle *hc, int32_t level, const void *x, int32_t x
         // stream order serialises reuse of this slot's buffers with its previous chunk
         const char *xs = static_cast<const char *>(x) + b0 * ldx * static_cast<int64_t>(sx);
         char *ys = static_cast<char *>(y) + b0 * ldy * static_cast<int64_t>(sy);
-        CUDA_TRY(cudaMemcpy2DAsync(sl.dx, L.n_src * sx, xs, ldx * sx, L.n_src * sx, nb,
-                                   cudaMemcpyHostToDevice, sl.stream));
+        if (ldx == L.n_src)      // contiguous rows: one linear copy runs at the full PCIe rate
+            CUDA_TRY(cudaMemcpyAsync(sl.dx, xs, static_cast<size_t>(nb) * L.n_src * sx, cudaMemcpyHostToDevice, sl.stream));
+        else
+            CUDA_TRY(cudaMemcpy2DAsync(sl.dx, L.n_src * sx, xs, ldx * sx, L.n_src * sx, nb,
+                                       cudaMemcpyHostToDevice, sl.stream));
         std::vector<JobSpec> specs{JobSpec{level, sl.dx, sl.dy, masked ? 1 : 0}};
         rc = launch_jobs(h, specs, x_dtype, y_dtype, nb, L.n_src, L.n_dst, remap_area_min, sl.stream);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpy2DAsync(ys, ldy * sy, sl.dy, L.n_dst * sy, L.n_dst * sy, nb,
-                                   cudaMemcpyDeviceToHost, sl.stream));
+        if (ldy == L.n_dst)
+            CUDA_TRY(cudaMemcpyAsync(ys, sl.dy, static_cast<size_t>(nb) * L.n_dst * sy, cudaMemcpyDeviceToHost, sl.stream));
+        else
+            CUDA_TRY(cudaMemcpy2DAsync(ys, ldy * sy, sl.dy, L.n_dst * sy, L.n_dst * sy, nb,
+                                       cudaMemcpyDeviceToHost, sl.stream));
     }
     for (int s = 0; s < nslots; ++s) CUDA_TRY(cudaStreamSynchronize(h->slots[s].stream));
     return SMM_OK;
