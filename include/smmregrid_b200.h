@@ -53,7 +53,7 @@ typedef struct smm_info {
     int32_t max_row_nnz;
     int32_t max_tile_segments;
     int32_t consumer_threads;    /* staged plan: link-holding threads per CTA (256 | 512)  */
-    int32_t reserved;
+    int32_t rows_reordered;      /* staged plan tiles rows re-ordered by mean source address */
     int64_t max_tile_elems;      /* largest staged source footprint of a tile (elements)  */
     int64_t sum_tile_elems;      /* sum of staged footprints: source elements one batch   */
                                  /* row pulls through TMA (>= touched columns)            */
@@ -168,6 +168,8 @@ int smm_host_plan_build(int64_t n_src, int64_t n_dst, int64_t nnz,
 int smm_host_plan_info(const smm_host_plan *p, smm_info *out, int64_t *n_segs_out);
 int smm_host_plan_copy(const smm_host_plan *p, int32_t *rowptr, int32_t *col, double *val,
                        int32_t *tiles, uint32_t *segs, double *wplan, uint16_t *iplan);
+/* rowmap [n_dst]: destination row held by every tile slot (only when info.rows_reordered). */
+int smm_host_plan_rowmap(const smm_host_plan *p, int32_t *rowmap);
 void smm_host_plan_free(smm_host_plan *p);
 
 /* Force a kernel family for subsequent applies (testing/benchmark aid): 0 = automatic,

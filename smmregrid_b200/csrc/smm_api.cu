@@ -48,6 +48,7 @@ struct LevelDev {
     Seg *segs = nullptr;
     double *wplan = nullptr;
     uint16_t *iplan = nullptr;
+    int32_t *rowmap = nullptr;
     int32_t *imask = nullptr;
     double *frac = nullptr;
     bool has_imask = false, has_frac = false;
@@ -88,7 +89,7 @@ int upload(T **dptr, const std::vector<T> &v, int64_t &bytes)
 void free_level(LevelDev &L)
 {
     cudaFree(L.rowptr); cudaFree(L.col); cudaFree(L.val);
-    cudaFree(L.tiles); cudaFree(L.segs); cudaFree(L.wplan); cudaFree(L.iplan);
+    cudaFree(L.tiles); cudaFree(L.segs); cudaFree(L.wplan); cudaFree(L.iplan); cudaFree(L.rowmap);
     cudaFree(L.imask); cudaFree(L.frac);
     L = LevelDev{};
 }
@@ -113,6 +114,7 @@ int upload_level(const HostCsr &csr, const HostPlan &plan, LevelDev &L)
         if ((rc = upload(&L.segs, plan.segs, L.device_bytes))) return rc;
         if ((rc = upload(&L.wplan, plan.wplan, L.device_bytes))) return rc;
         if ((rc = upload(&L.iplan, plan.iplan, L.device_bytes))) return rc;
+        if (!plan.rowmap.empty() && (rc = upload(&L.rowmap, plan.rowmap, L.device_bytes))) return rc;
     }
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&L.imask), static_cast<size_t>(L.n_dst) * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&L.frac), static_cast<size_t>(L.n_dst) * sizeof(double)));
@@ -254,7 +256,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
 
     auto fill_job = [&](const JobSpec &s, LevelJob &j) {
         const LevelDev &L = h->levels[s.level];
-        j.tiles = L.tiles; j.segs = L.segs; j.wplan = L.wplan; j.iplan = L.iplan;
+        j.tiles = L.tiles; j.segs = L.segs; j.wplan = L.wplan; j.iplan = L.iplan; j.rowmap = L.rowmap;
         j.rowptr = L.rowptr; j.col = L.col; j.val = L.val;
         j.imask = L.imask; j.frac = L.frac;
         j.x = s.x; j.y = s.y; j.masked = s.masked; j.pad = 0;
@@ -451,6 +453,7 @@ int smm_get_info(const smm_handle *h, int32_t level, smm_info *out)
     out->n_tiles = L.ntiles; out->max_row_nnz = L.max_row_nnz;
     out->max_tile_segments = L.max_segs; out->max_tile_elems = L.max_elems;
     out->consumer_threads = L.nct;
+    out->rows_reordered = L.rowmap ? 1 : 0;
     out->sum_tile_elems = L.sum_elems; out->touched_src = L.touched;
     out->device_bytes = L.device_bytes;
     return SMM_OK;
@@ -665,6 +668,7 @@ int smm_host_plan_info(const smm_host_plan *p, smm_info *out, int64_t *n_segs_ou
     out->max_row_nnz = p->csr.max_row_nnz;
     out->max_tile_segments = p->plan.max_tile_segments;
     out->consumer_threads = p->plan.nct;
+    out->rows_reordered = p->plan.rowmap.empty() ? 0 : 1;
     out->max_tile_elems = p->plan.max_tile_elems;
     out->sum_tile_elems = p->plan.sum_tile_elems;
     out->touched_src = p->csr.touched_src;
@@ -687,6 +691,13 @@ int smm_host_plan_copy(const smm_host_plan *p, int32_t *rowptr, int32_t *col, do
         cp(wplan, p->plan.wplan.data(), p->plan.wplan.size() * sizeof(double));
         cp(iplan, p->plan.iplan.data(), p->plan.iplan.size() * sizeof(uint16_t));
     }
+    return SMM_OK;
+}
+
+int smm_host_plan_rowmap(const smm_host_plan *p, int32_t *rowmap)
+{
+    if (!p || !rowmap) return fail(SMM_ERR_INVALID, "null argument");
+    if (!p->plan.rowmap.empty()) std::memcpy(rowmap, p->plan.rowmap.data(), p->plan.rowmap.size() * sizeof(int32_t));
     return SMM_OK;
 }
 

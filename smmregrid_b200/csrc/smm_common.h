@@ -44,6 +44,7 @@ struct LevelJob {
     const Seg *segs;
     const double *wplan;      // [ntiles][KPL][NCT] register image of the link weights
     const uint16_t *iplan;    // [ntiles][KPL][NCT] footprint-local element index per link
+    const int32_t *rowmap;    // destination row of every tile slot, or null: slot i of tile t is row t*R + i
     const int32_t *rowptr;    // CSR by destination row, columns ascending (reference order)
     const int32_t *col;
     const double *val;

@@ -269,8 +269,9 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
         const int r_in = tid / LPR;
         const int l_in = tid % LPR;
-        const int row = td.row0 + r_in;
         const bool valid = r_in < td.nrows;
+        // td.row0 is the tile's first slot; plans built on a re-ordered row sequence map slots to rows
+        const int row = (job.rowmap && valid) ? job.rowmap[td.row0 + r_in] : td.row0 + r_in;
 
         double w[KPL];
         uint32_t off[KPL];

@@ -112,7 +112,8 @@ int32_t default_consumer_threads(int64_t n_dst, int32_t lpr, int32_t sm_count)
     return tiles512 >= sm_count ? 512 : 256;
 }
 
-void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, HostPlan &plan)
+static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct,
+                               const std::vector<int32_t> *order, HostPlan &plan)
 {
     plan = HostPlan{};
     if (nct != 256 && nct != 512) nct = 256;
@@ -138,11 +139,20 @@ void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_
     std::vector<int32_t> cols;
     int64_t sum_blocks = 0;    // distinct aligned 8-element blocks touched, summed over tiles
     for (int64_t t = 0; t < ntiles; ++t) {
-        const int64_t r0 = t * R, r1 = std::min(n_dst, r0 + R);
-        const int32_t j0 = csr.rowptr[r0], j1 = csr.rowptr[r1];
-        cols.assign(csr.col.begin() + j0, csr.col.begin() + j1);
+        const int64_t r0 = t * R, r1 = std::min(n_dst, r0 + R);      // positions in the row order
+        auto row_at = [&](int64_t pos) -> int64_t { return order ? (*order)[pos] : pos; };
+        if (!order) {
+            cols.assign(csr.col.begin() + csr.rowptr[r0], csr.col.begin() + csr.rowptr[r1]);
+        } else {
+            cols.clear();
+            for (int64_t pos = r0; pos < r1; ++pos) {
+                const int64_t r = row_at(pos);
+                cols.insert(cols.end(), csr.col.begin() + csr.rowptr[r], csr.col.begin() + csr.rowptr[r + 1]);
+            }
+        }
         std::sort(cols.begin(), cols.end());
         cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+        plan.sum_tile_cols += static_cast<int64_t>(cols.size());
 
         TileDesc &td = plan.tiles[t];
         td = TileDesc{};
@@ -198,8 +208,9 @@ void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_
             for (auto &rr : rep) for (int32_t &v : rr) v = -1;
             for (auto &b : bucket) b.clear();
             for (int jr = 0; jr < rows_per_warp; ++jr) {
-                const int64_t r = r0 + static_cast<int64_t>(wi) * rows_per_warp + jr;
-                if (r >= r1) continue;
+                const int64_t pos = r0 + static_cast<int64_t>(wi) * rows_per_warp + jr;
+                if (pos >= r1) continue;
+                const int64_t r = row_at(pos);
                 const int32_t a = csr.rowptr[r], b = csr.rowptr[r + 1];
                 for (int32_t j = b - 1; j >= a; --j) {          // pushed in reverse: popped ascending
                     const uint32_t c = static_cast<uint32_t>(csr.col[j]);
@@ -310,7 +321,37 @@ void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_
         plan.why = "staged footprint over-reads the touched sectors";
         return;
     }
+    if (order) plan.rowmap = *order;
     plan.ok = true;
+}
+
+// staged cost of one batch row in element-equivalents: bytes moved + ~64 elements per bulk copy
+static double plan_cost(const HostPlan &p)
+{
+    return static_cast<double>(p.sum_tile_elems) + 64.0 * static_cast<double>(p.segs.size());
+}
+
+void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, HostPlan &plan)
+{
+    build_plan_ordered(csr, force_lpr, force_kpl, nct, nullptr, plan);
+    if (plan.lpr == 0 || csr.col.empty()) return;
+    // natural order good enough: footprints within 30 % of the columns actually touched
+    if (plan.ok && plan_cost(plan) <= 1.3 * static_cast<double>(plan.sum_tile_cols)) return;
+    // otherwise try rows sorted by the mean source address of their links
+    const int64_t n_dst = csr.n_dst;
+    std::vector<double> key(static_cast<size_t>(n_dst));
+    for (int64_t r = 0; r < n_dst; ++r) {
+        const int32_t a = csr.rowptr[r], b = csr.rowptr[r + 1];
+        double sum = 0.0;
+        for (int32_t j = a; j < b; ++j) sum += csr.col[j];
+        key[r] = b > a ? sum / (b - a) : 1e300;          // empty rows last
+    }
+    std::vector<int32_t> order(static_cast<size_t>(n_dst));
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return key[x] < key[y]; });
+    HostPlan alt;
+    build_plan_ordered(csr, force_lpr, force_kpl, nct, &order, alt);
+    if (alt.ok && (!plan.ok || plan_cost(alt) < 0.8 * plan_cost(plan))) plan = std::move(alt);
 }
 
 }  // namespace smm

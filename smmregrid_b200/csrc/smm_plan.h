@@ -32,11 +32,13 @@ struct HostPlan {
     int32_t nct = 0;          // consumer threads per CTA the register image is laid out for
     std::vector<TileDesc> tiles;
     std::vector<Seg> segs;
+    std::vector<int32_t> rowmap;   // empty: tile t holds rows [t*R, ...); else destination row of every tile slot
     std::vector<double> wplan;     // [ntiles][kpl][nct]
     std::vector<uint16_t> iplan;   // [ntiles][kpl][nct]
     int32_t max_tile_segments = 0;
     int64_t max_tile_elems = 0;
     int64_t sum_tile_elems = 0;
+    int64_t sum_tile_cols = 0;     // distinct source columns per tile, summed (the ideal footprint)
 };
 
 // Picks (lanes per row, links per lane) for a maximum row length; false if no staged
@@ -45,6 +47,10 @@ bool choose_lanes(int32_t max_row_nnz, int32_t &lpr, int32_t &kpl);
 
 // force_lpr/force_kpl > 0 impose a configuration shared by all levels of a 3-D weight set.
 // nct = consumer threads per CTA (256 or 512).
+// The natural plan tiles consecutive destination rows.  When that is unusable (scattered
+// footprints) a second plan is tried with the rows re-ordered by the mean source address of
+// their links, which turns locality-preserving unstructured orderings (HEALPix nested, Morton /
+// partition-ordered meshes) into compact per-tile footprints.
 void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, HostPlan &plan);
 
 // Consumer threads per CTA for a weight set: 512 (one CTA per SM, tiles twice as long, longer TMA

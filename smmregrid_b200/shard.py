@@ -71,3 +71,32 @@ def regrid_sharded(regridder, x, group=None, gather: bool = True, dst: Optional[
     if not isinstance(y_local, torch.Tensor):
         y_local = torch.from_numpy(y_local)
     return gather_to_host(y_local, B, group=group, dst=dst)
+
+
+def bind_to_gpu_numa(device_index: int) -> Optional[int]:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that pinned
+    host staging buffers (first-touch) and the H2D/D2H copies stay on the local socket.  On an
+    8-GPU box all ranks otherwise tend to allocate on one node and share its memory controllers
+    and inter-socket links.  Returns the node, or None when the topology cannot be read (then
+    nothing is changed).  Call before allocating pinned memory."""
+    import os
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None

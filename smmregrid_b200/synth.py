@@ -197,6 +197,73 @@ def scattered_weights(n_src, nlon_d, nlat_d, links_per_row=1, ordering="random",
                                 "map_method": "Nearest neighbor" if k == 1 else "Distance weighted avg"})
 
 
+# ------------------------------------------------------------- HEALPix (nested) source
+
+def _spread_bits(v):
+    """Interleave zeros between the low 16 bits (Morton helper)."""
+    v = v.astype(np.int64) & 0xffff
+    v = (v | (v << 8)) & 0x00ff00ff
+    v = (v | (v << 4)) & 0x0f0f0f0f
+    v = (v | (v << 2)) & 0x33333333
+    v = (v | (v << 1)) & 0x55555555
+    return v
+
+
+def ang2pix_nest(nside, lat_deg, lon_deg):
+    """HEALPix NESTED pixel index of points on the sphere (the standard ang2pix algorithm)."""
+    z = np.sin(np.asarray(lat_deg, dtype=np.float64) * DEG)
+    za = np.abs(z)
+    tt = (np.asarray(lon_deg, dtype=np.float64) % 360.0) / 90.0          # [0, 4)
+    # equatorial belt
+    t1, t2 = nside * (0.5 + tt), nside * z * 0.75
+    jp, jm = np.floor(t1 - t2).astype(np.int64), np.floor(t1 + t2).astype(np.int64)
+    ifp, ifm = jp // nside, jm // nside
+    face_eq = np.where(ifp == ifm, np.where(ifp == 4, 4, ifp + 4), np.where(ifp < ifm, ifp, ifm + 8))
+    ix_eq, iy_eq = jm & (nside - 1), nside - (jp & (nside - 1)) - 1
+    # polar caps
+    ntt = np.minimum(np.floor(tt).astype(np.int64), 3)
+    tp = tt - ntt
+    tmp = nside * np.sqrt(3.0 * (1.0 - za))
+    jpp = np.minimum(np.floor(tp * tmp).astype(np.int64), nside - 1)
+    jmp = np.minimum(np.floor((1.0 - tp) * tmp).astype(np.int64), nside - 1)
+    north = z >= 0
+    face_po = np.where(north, ntt, ntt + 8)
+    ix_po = np.where(north, nside - jmp - 1, jpp)
+    iy_po = np.where(north, nside - jpp - 1, jmp)
+    eq = za <= 2.0 / 3.0
+    face = np.where(eq, face_eq, face_po)
+    ix, iy = np.where(eq, ix_eq, ix_po), np.where(eq, iy_eq, iy_po)
+    return face * nside * nside + (_spread_bits(ix) | (_spread_bits(iy) << 1))
+
+
+def healpix_weights(nside, nlon_d, nlat_d, links_per_row=1) -> CdoWeights:
+    """nn (1 link/row) or dis-like (4 sample points per destination cell, inverse-distance-like
+    weights summing to 1) from a HEALPix NESTED source (12*nside^2 cells) to a regular lon-lat
+    grid.  Source addresses are scattered along a destination latitude row but compact for 2-D
+    neighbourhoods of destination cells -- the locality the row re-ordered plan exploits."""
+    n_src, n_dst = 12 * nside * nside, nlon_d * nlat_d
+    clat, _, _ = regular_lat(nlat_d)
+    clon, _, _ = regular_lon(nlon_d)
+    lat2d, lon2d = np.meshgrid(clat, clon, indexing="ij")
+    dlat, dlon = 180.0 / nlat_d, 360.0 / nlon_d
+    if links_per_row == 1:
+        src = ang2pix_nest(nside, lat2d, lon2d).reshape(n_dst, 1)
+        w = np.ones((n_dst, 1))
+    else:
+        offs = [(-0.3, -0.3, 0.35), (-0.3, 0.3, 0.3), (0.3, -0.3, 0.2), (0.3, 0.3, 0.15)]
+        src = np.stack([ang2pix_nest(nside, np.clip(lat2d + a * dlat, -89.999, 89.999), lon2d + b * dlon).ravel()
+                        for a, b, _ in offs], axis=1)
+        w = np.broadcast_to(np.array([o[2] for o in offs]), src.shape).copy()
+    dst = np.broadcast_to(np.arange(n_dst, dtype=np.int64)[:, None], src.shape)
+    src, dst, w = src.ravel(), dst.ravel(), w.ravel()
+    order = np.lexsort((src, dst))
+    v = _base_vars([n_src], [nlon_d, nlat_d], lat2d, lon2d, np.ones(n_src), np.ones(n_dst), np.ones(n_dst))
+    v.update(src_address=(src[order] + 1).astype(np.int32), dst_address=(dst[order] + 1).astype(np.int32),
+             remap_matrix=w[order].reshape(-1, 1))
+    return CdoWeights(v, attrs={"source_grid": f"hp{nside}_nested", "dest_grid": f"r{nlon_d}x{nlat_d}",
+                                "map_method": "Nearest neighbor" if links_per_row == 1 else "Distance weighted avg"})
+
+
 # --------------------------------------------------------------------- ORCA-like 3-D
 
 def ocean_masks(nlon_s, nlat_s, n_levels, seed=7):
@@ -273,4 +340,8 @@ def config_weights(name: str, scale: int = 1) -> CdoWeights:
         return scattered_weights(20971520 // (s * s), 1440 // s, 720 // s, 1, "random")
     if name == "C5dis":   # ~20M unstructured -> 0.25 deg remapdis
         return scattered_weights(20971520 // (s * s), 1440 // s, 720 // s, 4, "random")
+    if name == "C5hpnn":  # HEALPix nside 1024 nested (12.58M cells) -> 0.25 deg remapnn
+        return healpix_weights(1024 // s, 1440 // s, 720 // s, 1)
+    if name == "C5hpdis":  # same, 4 links/row
+        return healpix_weights(1024 // s, 1440 // s, 720 // s, 4)
     raise KeyError(name)

@@ -316,3 +316,27 @@ def test_errors(smm_lib, cuda):
     bad = w.assign(src_address=w["src_address"] + 10**6)
     with pytest.raises(ValueError):
         Regridder(weights=bad)
+
+
+@pytest.mark.parametrize("k", [1, 4])
+def test_healpix_nested_reordered_plan(smm_lib, oracle, cuda, k):
+    """HEALPix-nested source: the staged plan tiles rows re-ordered by mean source address
+    (row map indirection in the kernel); results must not depend on it."""
+    from smmregrid_b200 import synth
+    w = synth.healpix_weights(64, 180, 90, k)
+    n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+    B = 21
+    x = synth.synthetic_field((B, n_src), np.float32, seed=3, nan_mode="random")
+    frac = np.random.default_rng(0).random(n_dst)
+    imask = (np.random.default_rng(1).random(n_dst) > 0.1).astype(np.int32)
+    mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, imask, frac, 0.5, True)
+    h = _create(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    try:
+        info = _info(smm_lib, h)
+        assert info["kernel_name"] == "staged" and info["rows_reordered"] == 1
+        for kernel in (0, 2):
+            y = _apply(smm_lib, h, x, n_dst, np.float64, True, 0.5, imask, frac, kernel)
+            assert_parity(y, y_ref, RTOL_F64, f"healpix k={k} kernel={kernel}")
+    finally:
+        smm_lib.smm_destroy(h)

@@ -39,6 +39,10 @@ class HostPlan:
         _lib.check(lib.smm_host_plan_copy(h, self.rowptr.ctypes.data, self.col.ctypes.data, self.val.ctypes.data,
                                           self.tiles.ctypes.data, self.segs.ctypes.data,
                                           self.wplan.ctypes.data, self.iplan.ctypes.data))
+        self.rowmap = None
+        if inf.rows_reordered:
+            self.rowmap = np.empty(n_dst, np.int32)
+            _lib.check(lib.smm_host_plan_rowmap(h, self.rowmap.ctypes.data))
         lib.smm_host_plan_free(h)
 
     def emulate(self, x):
@@ -52,7 +56,10 @@ class HostPlan:
                 stage[:, d:d + ln] = x[:, s:s + ln]
             lane = (stage[:, self.iplan[t]] * self.wplan[t][None]).sum(axis=1)      # [B, nct]
             rows = lane.reshape(B, self.nct // lpr, lpr).sum(axis=2)
-            y[:, row0:row0 + nrows] = rows[:, :nrows]
+            if self.rowmap is None:
+                y[:, row0:row0 + nrows] = rows[:, :nrows]
+            else:                                      # row0 = first tile slot in the re-ordered sequence
+                y[:, self.rowmap[row0:row0 + nrows]] = rows[:, :nrows]
         return y
 
 
@@ -157,3 +164,34 @@ def test_address_range_errors(smm_lib):
         rc = smm_lib.smm_host_plan_build(10, 4, 1, s.ctypes.data, d.ctypes.data, w.ctypes.data, 1, 1, ctypes.byref(h))
         assert rc == _lib.SMM_ERR_RANGE
         assert b"outside the grids" in smm_lib.smm_last_error()
+
+
+def test_healpix_nested_source_gets_reordered_plan(smm_lib, oracle):
+    """A HEALPix-nested source is scattered along destination rows but compact in 2-D: the
+    natural plan is rejected, the plan on rows re-ordered by mean source address is staged."""
+    from smmregrid_b200 import synth
+    for k in (1, 4):
+        w = synth.healpix_weights(64, 180, 90, k)
+        n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+        # nearest-neighbour sanity: every pixel index valid, poles map to the polar faces
+        assert w["src_address"].min() >= 1 and w["src_address"].max() <= n_src
+        p = HostPlan(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+        assert p.info["kernel_name"] == "staged" and p.info["rows_reordered"] == 1, p.info
+        assert sorted(p.rowmap.tolist()) == list(range(n_dst))
+        t, sg = p.tiles, p.segs
+        assert t[:, 1].sum() == n_dst and (sg[:, 0] % 8 == 0).all()
+        x = np.random.default_rng(k).standard_normal((3, n_src)) + 5
+        mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+        assert_parity(p.emulate(x), oracle.apply_weights_c(x, mat, None, None, 0.0, False), 1e-12, f"hp{k}")
+
+
+def test_ang2pix_nest_known_values():
+    from smmregrid_b200.synth import ang2pix_nest
+    # nside = 1: the 12 base pixels; centres at lat +-41.81 (caps) and 0 (belt)
+    lat = np.array([41.81, 41.81, 41.81, 41.81, 0, 0, 0, 0, -41.81, -41.81, -41.81, -41.81])
+    lon = np.array([45, 135, 225, 315, 0, 90, 180, 270, 45, 135, 225, 315.0])
+    assert ang2pix_nest(1, lat, lon).tolist() == list(range(12))
+    # nside = 2: every pixel hit exactly by a dense sampling, indices within range
+    la, lo = np.meshgrid(np.linspace(-89.9, 89.9, 400), np.linspace(0.1, 359.9, 800), indexing="ij")
+    pix = ang2pix_nest(2, la, lo)
+    assert pix.min() == 0 and pix.max() == 47 and np.unique(pix).size == 48
