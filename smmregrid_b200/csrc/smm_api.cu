@@ -167,8 +167,8 @@ int launch_staged_t(int lpr, int kpl, int nct, dim3 grid, size_t smem, cudaStrea
         return SMM_OK;                                                                            \
     }
 #define SMM_CASE(L_, K_) SMM_CASE_N(L_, K_, 256) SMM_CASE_N(L_, K_, 512)
-    SMM_CASE(1, 4) SMM_CASE(2, 4) SMM_CASE(1, 16) SMM_CASE(2, 16) SMM_CASE(4, 16) SMM_CASE(8, 16)
-    SMM_CASE(16, 16) SMM_CASE(32, 16)
+    SMM_CASE(1, 4) SMM_CASE(2, 4) SMM_CASE(4, 4) SMM_CASE(1, 8) SMM_CASE(2, 8)
+    SMM_CASE(1, 16) SMM_CASE(2, 16) SMM_CASE(4, 16) SMM_CASE(8, 16) SMM_CASE(16, 16) SMM_CASE(32, 16)
 #undef SMM_CASE
 #undef SMM_CASE_N
     return fail(SMM_ERR_INVALID, "no staged kernel for this lane configuration");

@@ -8,6 +8,7 @@
 #include "smm_plan.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <numeric>
 
@@ -88,6 +89,10 @@ int build_csr(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t *src_addr
 
 bool choose_lanes(int32_t m, int32_t &lpr, int32_t &kpl)
 {
+    if (const char *e = std::getenv("SMM_FORCE_LANES")) {       // experiments: "lpr,kpl"
+        int a = 0, b = 0;
+        if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0 && m <= a * b) { lpr = a; kpl = b; return true; }
+    }
     if (m <= 4) { lpr = 1; kpl = 4; }
     else if (m <= 8) { lpr = 2; kpl = 4; }
     else if (m <= 16) { lpr = 1; kpl = 16; }
