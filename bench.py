@@ -191,6 +191,8 @@ def run_3d(args, rg, w, T, xdt, ydt, sx, sy, area_min, dev, g, world, rank, desc
     import torch
     from smmregrid_b200 import _lib
     L, n_src, n_dst = rg.weights_matrix.n_levels, rg.n_src, rg.n_dst
+    if args.kernel != "auto":
+        rg.weights_matrix.set_kernel(args.kernel)
     x = torch.empty((T, L, n_src), dtype=xdt, device=dev)
     x.normal_(10.0, 2.0, generator=g)
     land = torch.from_numpy(np.asarray(w["src_grid_imask"]).reshape(L, n_src) == 0).to(dev)
@@ -318,7 +320,8 @@ def main():
         xh = torch.empty((Be, n_src), dtype=xdt, pin_memory=True)
         xh.copy_(x[:Be])
         rg.regrid(xh[: min(Be, 8)])                               # warm the staging buffers
-        rg.regrid(xh)
+        for _ in range(3):                                        # and torch's pinned-host allocator cache
+            yh = rg.regrid(xh)
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
