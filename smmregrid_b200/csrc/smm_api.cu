@@ -8,7 +8,10 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <sched.h>
 
 #include "../../include/smmregrid_b200.h"
 #include "smm_kernels.cuh"
@@ -58,6 +61,8 @@ struct LevelDev {
 struct HostSlot {
     void *dx = nullptr, *dy = nullptr;
     size_t cap_x = 0, cap_y = 0;
+    void *px = nullptr, *py = nullptr;      // pinned bounce buffers for pageable host arrays
+    size_t cap_px = 0, cap_py = 0;
     cudaStream_t stream = nullptr;
 };
 
@@ -345,6 +350,48 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
     return SMM_OK;
 }
 
+// true when cudaMemcpyAsync can DMA straight from/to the pointer (pinned or registered)
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+int host_threads()
+{
+    cpu_set_t set;
+    int n = 1;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+    return std::max(1, std::min(n, env_int("SMM_HOST_COPY_THREADS", 8)));
+}
+
+// rows x row_bytes strided copy split over a few threads (pageable <-> pinned staging)
+void parallel_copy_rows(char *dst, size_t dst_stride, const char *src, size_t src_stride, size_t row_bytes,
+                        int64_t rows, int nthreads)
+{
+    const size_t total = static_cast<size_t>(rows) * row_bytes;
+    if (nthreads <= 1 || total < (size_t{4} << 20)) {
+        for (int64_t r = 0; r < rows; ++r) std::memcpy(dst + r * dst_stride, src + r * src_stride, row_bytes);
+        return;
+    }
+    // split by bytes so a few huge rows still spread over all threads
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t) {
+        pool.emplace_back([=]() {
+            const size_t lo = total * t / nthreads, hi = total * (t + 1) / nthreads;
+            size_t pos = lo;
+            while (pos < hi) {
+                const size_t r = pos / row_bytes, o = pos % row_bytes;
+                const size_t n = std::min(row_bytes - o, hi - pos);
+                std::memcpy(dst + r * dst_stride + o, src + r * src_stride + o, n);
+                pos += n;
+            }
+        });
+    }
+    for (auto &th : pool) th.join();
+}
+
 int check_dtypes(int32_t x_dtype, int32_t y_dtype)
 {
     if ((x_dtype != SMM_F32 && x_dtype != SMM_F64) || (y_dtype != SMM_F32 && y_dtype != SMM_F64))
@@ -431,6 +478,7 @@ int smm_destroy(smm_handle *h)
         for (LevelDev &L : h->levels) free_level(L);
         for (HostSlot &s : h->slots) {
             cudaFree(s.dx); cudaFree(s.dy);
+            cudaFreeHost(s.px); cudaFreeHost(s.py);
             if (s.stream) cudaStreamDestroy(s.stream);
         }
     }
@@ -575,17 +623,23 @@ int smm_apply_host(const smm_handle *hc, int32_t level, const void *x, int32_t x
     const LevelDev &L = h->levels[level];
     if (ldx < L.n_src || ldy < L.n_dst) return fail(SMM_ERR_INVALID, "ldx < n_src or ldy < n_dst");
     const size_t sx = x_dtype == SMM_F32 ? 4 : 8, sy = y_dtype == SMM_F32 ? 4 : 8;
+    // Pinned (or registered) host arrays are DMA'd directly.  Pageable arrays -- what numpy /
+    // xarray hand over -- go through pinned bounce buffers filled by a few host threads, which
+    // overlaps the host copy of chunk i+1 with the PCIe transfer and kernel of chunk i
+    // (cudaMemcpyAsync straight from pageable memory is synchronous and ~5x slower).
+    const bool x_pinned = is_pinned(x), y_pinned = is_pinned(y);
     if (chunk_rows <= 0) {
-        // ~256 MB of source per chunk (pipeline fill/drain of a few percent on multi-GB batches),
-        // at least 4 rows; SMM_HOST_CHUNK_MB overrides
-        const int64_t mb = std::max(1, env_int("SMM_HOST_CHUNK_MB", 256));
+        // ~256 MB of source per chunk for direct DMA (pipeline fill/drain of a few percent on
+        // multi-GB batches), ~64 MB when staging; at least 4 rows; SMM_HOST_CHUNK_MB overrides
+        const int64_t mb = std::max(1, env_int("SMM_HOST_CHUNK_MB", x_pinned ? 256 : 64));
         chunk_rows = std::max<int64_t>(4, (mb << 20) / std::max<int64_t>(1, L.n_src * sx));
     }
     chunk_rows = std::min(chunk_rows, B);
     std::lock_guard<std::mutex> lock(h->host_mu);
     DeviceGuard g(h->device);
-    const size_t need_x = static_cast<size_t>(chunk_rows) * L.n_src * sx;
-    const size_t need_y = static_cast<size_t>(chunk_rows) * L.n_dst * sy;
+    const size_t row_x = static_cast<size_t>(L.n_src) * sx, row_y = static_cast<size_t>(L.n_dst) * sy;
+    const size_t need_x = static_cast<size_t>(chunk_rows) * row_x;
+    const size_t need_y = static_cast<size_t>(chunk_rows) * row_y;
     const int nslots = B > chunk_rows ? 3 : 1;
     for (int s = 0; s < nslots; ++s) {
         HostSlot &sl = h->slots[s];
@@ -600,29 +654,65 @@ int smm_apply_host(const smm_handle *hc, int32_t level, const void *x, int32_t x
             CUDA_TRY(cudaMalloc(&sl.dy, need_y));
             sl.cap_y = need_y;
         }
+        if (!x_pinned && sl.cap_px < need_x) {
+            cudaFreeHost(sl.px); sl.px = nullptr; sl.cap_px = 0;
+            CUDA_TRY(cudaHostAlloc(&sl.px, need_x, cudaHostAllocDefault));
+            sl.cap_px = need_x;
+        }
+        if (!y_pinned && sl.cap_py < need_y) {
+            cudaFreeHost(sl.py); sl.py = nullptr; sl.cap_py = 0;
+            CUDA_TRY(cudaHostAlloc(&sl.py, need_y, cudaHostAllocDefault));
+            sl.cap_py = need_y;
+        }
     }
+    const int nthreads = host_threads();
+    struct Pending { char *ys = nullptr; int64_t nb = 0; };
+    Pending pending[3];
+    // drains a slot: waits for its D2H and, when staging, copies the rows out to the caller
+    auto drain = [&](int s) -> int {
+        HostSlot &sl = h->slots[s];
+        CUDA_TRY(cudaStreamSynchronize(sl.stream));
+        if (!y_pinned && pending[s].nb)
+            parallel_copy_rows(pending[s].ys, static_cast<size_t>(ldy) * sy, static_cast<const char *>(sl.py), row_y,
+                               row_y, pending[s].nb, 1);
+        pending[s] = Pending{};
+        return SMM_OK;
+    };
     int slot = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk_rows, slot = (slot + 1) % nslots) {
         const int64_t nb = std::min(chunk_rows, B - b0);
         HostSlot &sl = h->slots[slot];
-        // stream order serialises reuse of this slot's buffers with its previous chunk
         const char *xs = static_cast<const char *>(x) + b0 * ldx * static_cast<int64_t>(sx);
         char *ys = static_cast<char *>(y) + b0 * ldy * static_cast<int64_t>(sy);
-        if (ldx == L.n_src)      // contiguous rows: one linear copy runs at the full PCIe rate
-            CUDA_TRY(cudaMemcpyAsync(sl.dx, xs, static_cast<size_t>(nb) * L.n_src * sx, cudaMemcpyHostToDevice, sl.stream));
-        else
-            CUDA_TRY(cudaMemcpy2DAsync(sl.dx, L.n_src * sx, xs, ldx * sx, L.n_src * sx, nb,
-                                       cudaMemcpyHostToDevice, sl.stream));
+        if (!x_pinned || !y_pinned) {
+            // the bounce buffers of this slot are reused: its previous chunk must be complete
+            if ((rc = drain(slot))) return rc;
+        }
+        if (x_pinned) {
+            // stream order serialises reuse of this slot's device buffers with its previous chunk
+            if (ldx == L.n_src)      // contiguous rows: one linear copy runs at the full PCIe rate
+                CUDA_TRY(cudaMemcpyAsync(sl.dx, xs, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, sl.stream));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync(sl.dx, row_x, xs, ldx * sx, row_x, nb, cudaMemcpyHostToDevice, sl.stream));
+        } else {
+            parallel_copy_rows(static_cast<char *>(sl.px), row_x, xs, static_cast<size_t>(ldx) * sx, row_x, nb, nthreads);
+            CUDA_TRY(cudaMemcpyAsync(sl.dx, sl.px, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, sl.stream));
+        }
         std::vector<JobSpec> specs{JobSpec{level, sl.dx, sl.dy, masked ? 1 : 0}};
         rc = launch_jobs(h, specs, x_dtype, y_dtype, nb, L.n_src, L.n_dst, remap_area_min, sl.stream);
         if (rc) return rc;
-        if (ldy == L.n_dst)
-            CUDA_TRY(cudaMemcpyAsync(ys, sl.dy, static_cast<size_t>(nb) * L.n_dst * sy, cudaMemcpyDeviceToHost, sl.stream));
-        else
-            CUDA_TRY(cudaMemcpy2DAsync(ys, ldy * sy, sl.dy, L.n_dst * sy, L.n_dst * sy, nb,
-                                       cudaMemcpyDeviceToHost, sl.stream));
+        if (y_pinned) {
+            if (ldy == L.n_dst)
+                CUDA_TRY(cudaMemcpyAsync(ys, sl.dy, static_cast<size_t>(nb) * row_y, cudaMemcpyDeviceToHost, sl.stream));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync(ys, ldy * sy, sl.dy, row_y, row_y, nb, cudaMemcpyDeviceToHost, sl.stream));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(sl.py, sl.dy, static_cast<size_t>(nb) * row_y, cudaMemcpyDeviceToHost, sl.stream));
+            pending[slot] = Pending{ys, nb};
+        }
     }
-    for (int s = 0; s < nslots; ++s) CUDA_TRY(cudaStreamSynchronize(h->slots[s].stream));
+    for (int s = 0; s < nslots; ++s)
+        if ((rc = drain(s))) return rc;
     return SMM_OK;
 }
 
