@@ -153,6 +153,16 @@ int smm_apply_host(const smm_handle *h, int32_t level,
 
 
 /*
+ * smm_apply_levels for HOST buffers in the canonical layout: x [B, n_sel, n_src] and
+ * y [B, n_sel, n_dst], both contiguous (data level i uses weight level level_index[i]); same
+ * streaming pipeline as smm_apply_host, chunked over B.  Synchronous.
+ */
+int smm_apply_levels_host(const smm_handle *h, int32_t n_sel, const int32_t *level_index,
+                          const void *x, int32_t x_dtype, int64_t B,
+                          void *y, int32_t y_dtype,
+                          const uint8_t *masked, double remap_area_min, int64_t chunk_rows);
+
+/*
  * Host-only introspection of the operator construction (no device needed): builds the
  * same CSR + tile plan smm_create uploads, so the host logic can be verified on a CPU-only
  * machine.  No compute entry point exists on the host side.

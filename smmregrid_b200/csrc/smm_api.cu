@@ -410,6 +410,107 @@ int check_level(const smm_handle *h, int32_t level)
 
 }  // namespace
 
+namespace {
+
+// Host <-> device streaming pipeline shared by smm_apply_host and smm_apply_levels_host.
+// A batch row is `row_x` bytes of source (rows `x_stride` bytes apart) and `row_y` bytes of
+// result; `launch(dx, dy, nb, stream)` applies the operator to nb batch rows held contiguously
+// on the device.  Pinned (or registered) host arrays are DMA'd directly.  Pageable arrays --
+// what numpy / xarray hand over -- go through pinned bounce buffers filled by a few host
+// threads, which overlaps the host copy of chunk i+1 with the PCIe transfer and kernel of
+// chunk i (cudaMemcpyAsync straight from pageable memory is synchronous and ~3-5x slower).
+template <typename Launch>
+int host_pipeline(smm_handle *h, const void *x, size_t row_x, size_t x_stride, void *y, size_t row_y,
+                  size_t y_stride, int64_t B, int64_t chunk_rows, Launch launch)
+{
+    const bool x_pinned = is_pinned(x), y_pinned = is_pinned(y);
+    if (chunk_rows <= 0) {
+        // ~256 MB of source per chunk for direct DMA (pipeline fill/drain of a few percent on
+        // multi-GB batches), ~64 MB when staging; at least 4 rows; SMM_HOST_CHUNK_MB overrides
+        const int64_t mb = std::max(1, env_int("SMM_HOST_CHUNK_MB", x_pinned ? 256 : 64));
+        chunk_rows = std::max<int64_t>(4, (mb << 20) / std::max<int64_t>(1, static_cast<int64_t>(row_x)));
+    }
+    chunk_rows = std::min(chunk_rows, B);
+    std::lock_guard<std::mutex> lock(h->host_mu);
+    DeviceGuard g(h->device);
+    const size_t need_x = static_cast<size_t>(chunk_rows) * row_x;
+    const size_t need_y = static_cast<size_t>(chunk_rows) * row_y;
+    const int nslots = B > chunk_rows ? 3 : 1;
+    for (int s = 0; s < nslots; ++s) {
+        HostSlot &sl = h->slots[s];
+        if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (sl.cap_x < need_x) {
+            cudaFree(sl.dx); sl.dx = nullptr; sl.cap_x = 0;
+            CUDA_TRY(cudaMalloc(&sl.dx, need_x));
+            sl.cap_x = need_x;
+        }
+        if (sl.cap_y < need_y) {
+            cudaFree(sl.dy); sl.dy = nullptr; sl.cap_y = 0;
+            CUDA_TRY(cudaMalloc(&sl.dy, need_y));
+            sl.cap_y = need_y;
+        }
+        if (!x_pinned && sl.cap_px < need_x) {
+            cudaFreeHost(sl.px); sl.px = nullptr; sl.cap_px = 0;
+            CUDA_TRY(cudaHostAlloc(&sl.px, need_x, cudaHostAllocDefault));
+            sl.cap_px = need_x;
+        }
+        if (!y_pinned && sl.cap_py < need_y) {
+            cudaFreeHost(sl.py); sl.py = nullptr; sl.cap_py = 0;
+            CUDA_TRY(cudaHostAlloc(&sl.py, need_y, cudaHostAllocDefault));
+            sl.cap_py = need_y;
+        }
+    }
+    const int nthreads = host_threads();
+    struct Pending { char *ys = nullptr; int64_t nb = 0; };
+    Pending pending[3];
+    // drains a slot: waits for its D2H and, when staging, copies the rows out to the caller
+    auto drain = [&](int s) -> int {
+        HostSlot &sl = h->slots[s];
+        CUDA_TRY(cudaStreamSynchronize(sl.stream));
+        if (!y_pinned && pending[s].nb)
+            parallel_copy_rows(pending[s].ys, y_stride, static_cast<const char *>(sl.py), row_y, row_y,
+                               pending[s].nb, 1);
+        pending[s] = Pending{};
+        return SMM_OK;
+    };
+    int rc, slot = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk_rows, slot = (slot + 1) % nslots) {
+        const int64_t nb = std::min(chunk_rows, B - b0);
+        HostSlot &sl = h->slots[slot];
+        const char *xs = static_cast<const char *>(x) + static_cast<size_t>(b0) * x_stride;
+        char *ys = static_cast<char *>(y) + static_cast<size_t>(b0) * y_stride;
+        if (!x_pinned || !y_pinned) {
+            // the bounce buffers of this slot are reused: its previous chunk must be complete
+            if ((rc = drain(slot))) return rc;
+        }
+        if (x_pinned) {
+            // stream order serialises reuse of this slot's device buffers with its previous chunk
+            if (x_stride == row_x)   // contiguous rows: one linear copy runs at the full PCIe rate
+                CUDA_TRY(cudaMemcpyAsync(sl.dx, xs, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, sl.stream));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync(sl.dx, row_x, xs, x_stride, row_x, nb, cudaMemcpyHostToDevice, sl.stream));
+        } else {
+            parallel_copy_rows(static_cast<char *>(sl.px), row_x, xs, x_stride, row_x, nb, nthreads);
+            CUDA_TRY(cudaMemcpyAsync(sl.dx, sl.px, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, sl.stream));
+        }
+        if ((rc = launch(sl.dx, sl.dy, nb, sl.stream))) return rc;
+        if (y_pinned) {
+            if (y_stride == row_y)
+                CUDA_TRY(cudaMemcpyAsync(ys, sl.dy, static_cast<size_t>(nb) * row_y, cudaMemcpyDeviceToHost, sl.stream));
+            else
+                CUDA_TRY(cudaMemcpy2DAsync(ys, y_stride, sl.dy, row_y, row_y, nb, cudaMemcpyDeviceToHost, sl.stream));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(sl.py, sl.dy, static_cast<size_t>(nb) * row_y, cudaMemcpyDeviceToHost, sl.stream));
+            pending[slot] = Pending{ys, nb};
+        }
+    }
+    for (int s = 0; s < nslots; ++s)
+        if ((rc = drain(s))) return rc;
+    return SMM_OK;
+}
+
+}  // namespace
+
 // ====================================================================== C ABI
 
 extern "C" {
@@ -619,101 +720,49 @@ int smm_apply_host(const smm_handle *hc, int32_t level, const void *x, int32_t x
     if (B < 0) return fail(SMM_ERR_INVALID, "B must be >= 0");
     if (B == 0) return SMM_OK;
     if (!x || !y) return fail(SMM_ERR_INVALID, "null x or y");
+    if (!(remap_area_min >= 0.0 && remap_area_min <= 1.0))
+        return fail(SMM_ERR_INVALID, "The remap_area_min provided must be between 0.0 and 1.0");
     smm_handle *h = const_cast<smm_handle *>(hc);
     const LevelDev &L = h->levels[level];
     if (ldx < L.n_src || ldy < L.n_dst) return fail(SMM_ERR_INVALID, "ldx < n_src or ldy < n_dst");
     const size_t sx = x_dtype == SMM_F32 ? 4 : 8, sy = y_dtype == SMM_F32 ? 4 : 8;
-    // Pinned (or registered) host arrays are DMA'd directly.  Pageable arrays -- what numpy /
-    // xarray hand over -- go through pinned bounce buffers filled by a few host threads, which
-    // overlaps the host copy of chunk i+1 with the PCIe transfer and kernel of chunk i
-    // (cudaMemcpyAsync straight from pageable memory is synchronous and ~5x slower).
-    const bool x_pinned = is_pinned(x), y_pinned = is_pinned(y);
-    if (chunk_rows <= 0) {
-        // ~256 MB of source per chunk for direct DMA (pipeline fill/drain of a few percent on
-        // multi-GB batches), ~64 MB when staging; at least 4 rows; SMM_HOST_CHUNK_MB overrides
-        const int64_t mb = std::max(1, env_int("SMM_HOST_CHUNK_MB", x_pinned ? 256 : 64));
-        chunk_rows = std::max<int64_t>(4, (mb << 20) / std::max<int64_t>(1, L.n_src * sx));
-    }
-    chunk_rows = std::min(chunk_rows, B);
-    std::lock_guard<std::mutex> lock(h->host_mu);
-    DeviceGuard g(h->device);
-    const size_t row_x = static_cast<size_t>(L.n_src) * sx, row_y = static_cast<size_t>(L.n_dst) * sy;
-    const size_t need_x = static_cast<size_t>(chunk_rows) * row_x;
-    const size_t need_y = static_cast<size_t>(chunk_rows) * row_y;
-    const int nslots = B > chunk_rows ? 3 : 1;
-    for (int s = 0; s < nslots; ++s) {
-        HostSlot &sl = h->slots[s];
-        if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-        if (sl.cap_x < need_x) {
-            cudaFree(sl.dx); sl.dx = nullptr; sl.cap_x = 0;
-            CUDA_TRY(cudaMalloc(&sl.dx, need_x));
-            sl.cap_x = need_x;
-        }
-        if (sl.cap_y < need_y) {
-            cudaFree(sl.dy); sl.dy = nullptr; sl.cap_y = 0;
-            CUDA_TRY(cudaMalloc(&sl.dy, need_y));
-            sl.cap_y = need_y;
-        }
-        if (!x_pinned && sl.cap_px < need_x) {
-            cudaFreeHost(sl.px); sl.px = nullptr; sl.cap_px = 0;
-            CUDA_TRY(cudaHostAlloc(&sl.px, need_x, cudaHostAllocDefault));
-            sl.cap_px = need_x;
-        }
-        if (!y_pinned && sl.cap_py < need_y) {
-            cudaFreeHost(sl.py); sl.py = nullptr; sl.cap_py = 0;
-            CUDA_TRY(cudaHostAlloc(&sl.py, need_y, cudaHostAllocDefault));
-            sl.cap_py = need_y;
-        }
-    }
-    const int nthreads = host_threads();
-    struct Pending { char *ys = nullptr; int64_t nb = 0; };
-    Pending pending[3];
-    // drains a slot: waits for its D2H and, when staging, copies the rows out to the caller
-    auto drain = [&](int s) -> int {
-        HostSlot &sl = h->slots[s];
-        CUDA_TRY(cudaStreamSynchronize(sl.stream));
-        if (!y_pinned && pending[s].nb)
-            parallel_copy_rows(pending[s].ys, static_cast<size_t>(ldy) * sy, static_cast<const char *>(sl.py), row_y,
-                               row_y, pending[s].nb, 1);
-        pending[s] = Pending{};
-        return SMM_OK;
-    };
-    int slot = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += chunk_rows, slot = (slot + 1) % nslots) {
-        const int64_t nb = std::min(chunk_rows, B - b0);
-        HostSlot &sl = h->slots[slot];
-        const char *xs = static_cast<const char *>(x) + b0 * ldx * static_cast<int64_t>(sx);
-        char *ys = static_cast<char *>(y) + b0 * ldy * static_cast<int64_t>(sy);
-        if (!x_pinned || !y_pinned) {
-            // the bounce buffers of this slot are reused: its previous chunk must be complete
-            if ((rc = drain(slot))) return rc;
-        }
-        if (x_pinned) {
-            // stream order serialises reuse of this slot's device buffers with its previous chunk
-            if (ldx == L.n_src)      // contiguous rows: one linear copy runs at the full PCIe rate
-                CUDA_TRY(cudaMemcpyAsync(sl.dx, xs, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, sl.stream));
-            else
-                CUDA_TRY(cudaMemcpy2DAsync(sl.dx, row_x, xs, ldx * sx, row_x, nb, cudaMemcpyHostToDevice, sl.stream));
-        } else {
-            parallel_copy_rows(static_cast<char *>(sl.px), row_x, xs, static_cast<size_t>(ldx) * sx, row_x, nb, nthreads);
-            CUDA_TRY(cudaMemcpyAsync(sl.dx, sl.px, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, sl.stream));
-        }
-        std::vector<JobSpec> specs{JobSpec{level, sl.dx, sl.dy, masked ? 1 : 0}};
-        rc = launch_jobs(h, specs, x_dtype, y_dtype, nb, L.n_src, L.n_dst, remap_area_min, sl.stream);
-        if (rc) return rc;
-        if (y_pinned) {
-            if (ldy == L.n_dst)
-                CUDA_TRY(cudaMemcpyAsync(ys, sl.dy, static_cast<size_t>(nb) * row_y, cudaMemcpyDeviceToHost, sl.stream));
-            else
-                CUDA_TRY(cudaMemcpy2DAsync(ys, ldy * sy, sl.dy, row_y, row_y, nb, cudaMemcpyDeviceToHost, sl.stream));
-        } else {
-            CUDA_TRY(cudaMemcpyAsync(sl.py, sl.dy, static_cast<size_t>(nb) * row_y, cudaMemcpyDeviceToHost, sl.stream));
-            pending[slot] = Pending{ys, nb};
-        }
-    }
-    for (int s = 0; s < nslots; ++s)
-        if ((rc = drain(s))) return rc;
-    return SMM_OK;
+    return host_pipeline(h, x, L.n_src * sx, ldx * sx, y, L.n_dst * sy, ldy * sy, B, chunk_rows,
+                         [&](void *dx, void *dy, int64_t nb, cudaStream_t st) -> int {
+                             std::vector<JobSpec> specs{JobSpec{level, dx, dy, masked ? 1 : 0}};
+                             return launch_jobs(h, specs, x_dtype, y_dtype, nb, L.n_src, L.n_dst, remap_area_min, st);
+                         });
+}
+
+int smm_apply_levels_host(const smm_handle *hc, int32_t n_sel, const int32_t *level_index, const void *x,
+                          int32_t x_dtype, int64_t B, void *y, int32_t y_dtype, const uint8_t *masked,
+                          double remap_area_min, int64_t chunk_rows)
+{
+    if (!hc) return fail(SMM_ERR_INVALID, "null handle");
+    int rc;
+    if ((rc = check_dtypes(x_dtype, y_dtype))) return rc;
+    if (n_sel < 0 || B < 0) return fail(SMM_ERR_INVALID, "n_sel and B must be >= 0");
+    if (n_sel == 0 || B == 0) return SMM_OK;
+    if (!level_index || !x || !y) return fail(SMM_ERR_INVALID, "null level_index, x or y");
+    if (!(remap_area_min >= 0.0 && remap_area_min <= 1.0))
+        return fail(SMM_ERR_INVALID, "The remap_area_min provided must be between 0.0 and 1.0");
+    for (int32_t i = 0; i < n_sel; ++i)
+        if ((rc = check_level(hc, level_index[i]))) return rc;
+    smm_handle *h = const_cast<smm_handle *>(hc);
+    const int64_t n_src = h->levels[0].n_src, n_dst = h->levels[0].n_dst;
+    const size_t sx = x_dtype == SMM_F32 ? 4 : 8, sy = y_dtype == SMM_F32 ? 4 : 8;
+    const size_t row_x = static_cast<size_t>(n_sel) * n_src * sx, row_y = static_cast<size_t>(n_sel) * n_dst * sy;
+    return host_pipeline(h, x, row_x, row_x, y, row_y, row_y, B, chunk_rows,
+                         [&](void *dx, void *dy, int64_t nb, cudaStream_t st) -> int {
+                             std::vector<JobSpec> specs;
+                             specs.reserve(static_cast<size_t>(n_sel));
+                             for (int32_t i = 0; i < n_sel; ++i)
+                                 specs.push_back(JobSpec{level_index[i],
+                                                         static_cast<const char *>(dx) + static_cast<size_t>(i) * n_src * sx,
+                                                         static_cast<char *>(dy) + static_cast<size_t>(i) * n_dst * sy,
+                                                         masked ? (masked[i] ? 1 : 0) : 0});
+                             return launch_jobs(h, specs, x_dtype, y_dtype, nb, static_cast<int64_t>(n_sel) * n_src,
+                                                static_cast<int64_t>(n_sel) * n_dst, remap_area_min, st);
+                         });
 }
 
 // ---- host-only introspection (no device): CSR + plan exactly as smm_create builds them

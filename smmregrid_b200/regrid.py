@@ -170,8 +170,9 @@ class Regridder(object):
         was_numpy = isinstance(source_data, np.ndarray)
         x = torch.from_numpy(np.ascontiguousarray(source_data)) if was_numpy else source_data
         host_in = not x.is_cuda
+        if host_in:
+            return self._regrid3d_host(x, la, nkept, Ld, widx, masked, was_numpy)
         dev = torch.device("cuda", self.device)
-        x = x.to(dev, non_blocking=True)
         # canonical layout [T, L, n_src]: level axis last among the kept ones
         x = torch.movedim(x, la, nkept - 1)
         kept_shape = tuple(x.shape[:nkept - 1])
@@ -197,10 +198,28 @@ class Regridder(object):
             y = y.reshape(kept_shape + (Ld,) + self.tgt_shape)
         else:                   # concat on a new leading axis (regrid.py:410)
             y = y.reshape((Ld,) + kept_shape + self.tgt_shape)
-        if host_in:
-            y = y.cpu()
-            return y.numpy() if was_numpy else y
         return y
+
+    def _regrid3d_host(self, x, la, nkept, Ld, widx, masked, was_numpy):
+        """regrid3d for host data: streamed through the library in chunks of the leading kept
+        axes (pinned bounce buffers for pageable arrays), never holding the whole field on the
+        device."""
+        torch = _torch()
+        x = torch.movedim(x, la, nkept - 1)                    # canonical [T, L, n_src]
+        kept_shape = tuple(x.shape[:nkept - 1])
+        T = int(np.prod(kept_shape)) if kept_shape else 1
+        x = x.reshape(T, Ld, self.n_src).contiguous()
+        y = torch.empty((T, Ld, self.n_dst), dtype=self._out_torch_dtype(x.dtype), pin_memory=True)
+        _lib.check(_lib.load().smm_apply_levels_host(
+            self.weights_matrix.handle, Ld, widx.ctypes.data_as(ctypes.c_void_p),
+            ctypes.c_void_p(x.data_ptr()), _np_dtype_code(_np_of(x.dtype)), T,
+            ctypes.c_void_p(y.data_ptr()), _np_dtype_code(_np_of(y.dtype)),
+            masked.ctypes.data_as(ctypes.c_void_p), self.remap_area_min, 0))
+        if self.transpose:      # [kept..., L, tgt...]  (regrid.py:420-427)
+            y = y.reshape(kept_shape + (Ld,) + self.tgt_shape)
+        else:                   # level axis first, as xarray.concat leaves it (regrid.py:410)
+            y = torch.movedim(y, 1, 0).reshape((Ld,) + kept_shape + self.tgt_shape)
+        return y.numpy() if was_numpy else y
 
     def apply_weights(self, source_data, weights=None, weights_matrix=None, masked=True,
                       horizontal_dims=None, level: int = 0):
