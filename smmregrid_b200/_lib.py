@@ -66,7 +66,8 @@ class SmmError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """In-tree library; SMM_LIB_PATH points at an alternative build (experiments)."""
+    return os.environ.get("SMM_LIB_PATH") or _build.LIB_PATH
 
 
 def load():

@@ -166,7 +166,7 @@ int launch_staged_t(int lpr, int kpl, int nct, dim3 grid, size_t smem, cudaStrea
         auto kfn = staged_kernel<TX, TY, L_, K_, N_>;                                             \
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                       static_cast<int>(smem)));                                   \
-        kfn<<<grid, N_ + 32 * kProducerWarps, smem, st>>>(jb, a);                                 \
+        kfn<<<grid, N_ + 32 * producer_warps(N_), smem, st>>>(jb, a);                             \
         CUDA_TRY(cudaGetLastError());                                                             \
         g_launches.fetch_add(1, std::memory_order_relaxed);                                       \
         return SMM_OK;                                                                            \

@@ -194,14 +194,19 @@ __device__ __forceinline__ bool not_finite(double v) { return !(fabs(v) <= 1.797
 // Registers: two CTAs of 12 warps per SM = 6 warps per SM sub-partition -> 80 registers per
 // thread at launch; the producer warpgroup then shrinks to 40 and the consumer warpgroups
 // grow to 96 (setmaxnreg), which the link weights + offsets held in registers need.
-constexpr int kProducerWarps = 4;
+// producer warps per CTA: 4 with NCT = 256 (two CTAs per SM), SMM_PRODUCERS_512 with NCT = 512
+#ifndef SMM_PRODUCERS_512
+#define SMM_PRODUCERS_512 4
+#endif
+__host__ __device__ constexpr int producer_warps(int nct) { return nct == 512 ? SMM_PRODUCERS_512 : 4; }
 constexpr int kProducerRegs = 40;
 constexpr int kConsumerRegs = 96;
 
 template <typename TX, typename TY, int LPR, int KPL, int NCT>
-__global__ void __launch_bounds__(NCT + 32 * kProducerWarps, NCT == 256 ? 2 : 1)
+__global__ void __launch_bounds__(NCT + 32 * producer_warps(NCT), NCT == 256 ? 2 : 1)
 staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ ApplyArgs a)
 {
+    constexpr int kProducerWarps = producer_warps(NCT);
     constexpr int kThreads = NCT + 32 * kProducerWarps;
     constexpr int kConsumerWarps = NCT / 32;
     extern __shared__ __align__(128) unsigned char smem[];

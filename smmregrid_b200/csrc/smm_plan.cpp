@@ -10,7 +10,11 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <numeric>
+#include <thread>
+
+#include <sched.h>
 
 #include "../../include/smmregrid_b200.h"
 
@@ -141,9 +145,18 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
     plan.wplan.assign(static_cast<size_t>(ntiles) * kpl * nct, 0.0);
     plan.iplan.assign(static_cast<size_t>(ntiles) * kpl * nct, 0);
 
+    // Tiles are independent: a few host threads each build a contiguous range of tiles into
+    // their own segment list; the lists are stitched together afterwards.
+    struct Part {
+        int64_t t0 = 0, t1 = 0;
+        std::vector<Seg> segs;
+        int64_t sum_cols = 0, sum_blocks = 0, sum_elems = 0, max_elems = 0;
+        int32_t max_segs = 0;
+        bool too_big = false, failed = false;
+    };
+    auto work = [&](Part &out) {
     std::vector<int32_t> cols;
-    int64_t sum_blocks = 0;    // distinct aligned 8-element blocks touched, summed over tiles
-    for (int64_t t = 0; t < ntiles; ++t) {
+    for (int64_t t = out.t0; t < out.t1; ++t) {
         const int64_t r0 = t * R, r1 = std::min(n_dst, r0 + R);      // positions in the row order
         auto row_at = [&](int64_t pos) -> int64_t { return order ? (*order)[pos] : pos; };
         if (!order) {
@@ -157,24 +170,24 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
         }
         std::sort(cols.begin(), cols.end());
         cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
-        plan.sum_tile_cols += static_cast<int64_t>(cols.size());
+        out.sum_cols += static_cast<int64_t>(cols.size());
 
         TileDesc &td = plan.tiles[t];
         td = TileDesc{};
         td.row0 = static_cast<int32_t>(r0);
         td.nrows = static_cast<int32_t>(r1 - r0);
-        td.seg0 = static_cast<int32_t>(plan.segs.size());
+        td.seg0 = static_cast<int32_t>(out.segs.size());   // index in this part; rebased when stitching
         int64_t cs = -1, ce = -1, last_block = -1;
         uint32_t off = 0;
         auto flush = [&]() {
             if (cs < 0) return;
             Seg sg{static_cast<uint32_t>(cs), off, static_cast<uint32_t>(ce - cs), 0};
-            plan.segs.push_back(sg);
+            out.segs.push_back(sg);
             off += sg.len;
         };
         for (int32_t c : cols) {
             const int64_t blk = c / kSegAlign;
-            if (blk != last_block) { ++sum_blocks; last_block = blk; }
+            if (blk != last_block) { ++out.sum_blocks; last_block = blk; }
             if (cs >= 0 && c < ce) continue;
             const int64_t s_al = blk * kSegAlign;
             const int64_t e_al = std::min<int64_t>((blk + 1) * kSegAlign, n_src);
@@ -186,12 +199,12 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
             }
         }
         flush();
-        td.nseg = static_cast<int32_t>(plan.segs.size()) - td.seg0;
+        td.nseg = static_cast<int32_t>(out.segs.size()) - td.seg0;
         td.elems = static_cast<int32_t>(off);
-        plan.max_tile_segments = std::max(plan.max_tile_segments, td.nseg);
-        plan.max_tile_elems = std::max<int64_t>(plan.max_tile_elems, off);
-        plan.sum_tile_elems += off;
-        if (off > 65535u) { plan.why = "tile footprint exceeds 16-bit local indices"; return; }
+        out.max_segs = std::max(out.max_segs, td.nseg);
+        out.max_elems = std::max<int64_t>(out.max_elems, off);
+        out.sum_elems += off;
+        if (off > 65535u) { out.too_big = true; return; }
 
         // Register image.  A row's links may sit in any (lane, slot) of the row's lane group --
         // the kernel sums them all -- so the assignment is chosen to spread each warp-wide
@@ -200,7 +213,7 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
         // lane's row still has to place.  Unplaced slots carry weight 0 and re-read the row's
         // first link (the fast path skips the non-finite test, so a padded slot must never see
         // a NaN the row does not own).
-        const Seg *sb = plan.segs.data() + td.seg0;
+        const Seg *sb = out.segs.data() + td.seg0;
         const size_t tbase = static_cast<size_t>(t) * kpl * nct;
         const int rows_per_warp = 32 / lpr;
         const int nwarps = nct / 32;
@@ -314,8 +327,42 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
                 }
             }
             for (int jr = 0; jr < rows_per_warp; ++jr)
-                if (remaining[jr] != 0) { plan.why = "internal: link placement failed"; return; }
+                if (remaining[jr] != 0) { out.failed = true; return; }
         }
+    }
+    };
+
+    int nthreads = 1;
+    {
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) nthreads = CPU_COUNT(&set);
+        if (const char *e = std::getenv("SMM_PLAN_THREADS")) nthreads = std::atoi(e);
+        nthreads = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>({nthreads, 16, ntiles / 32})));
+    }
+    std::vector<Part> parts(static_cast<size_t>(nthreads));
+    for (int i = 0; i < nthreads; ++i) {
+        parts[i].t0 = ntiles * i / nthreads;
+        parts[i].t1 = ntiles * (i + 1) / nthreads;
+    }
+    if (nthreads == 1) {
+        work(parts[0]);
+    } else {
+        std::vector<std::thread> pool;
+        for (int i = 0; i < nthreads; ++i) pool.emplace_back(work, std::ref(parts[i]));
+        for (auto &th : pool) th.join();
+    }
+    int64_t sum_blocks = 0;
+    for (Part &pt : parts) {
+        if (pt.too_big) { plan.why = "tile footprint exceeds 16-bit local indices"; return; }
+        if (pt.failed) { plan.why = "internal: link placement failed"; return; }
+        const int32_t base = static_cast<int32_t>(plan.segs.size());
+        for (int64_t t = pt.t0; t < pt.t1; ++t) plan.tiles[t].seg0 += base;
+        plan.segs.insert(plan.segs.end(), pt.segs.begin(), pt.segs.end());
+        plan.sum_tile_cols += pt.sum_cols;
+        plan.sum_tile_elems += pt.sum_elems;
+        plan.max_tile_elems = std::max(plan.max_tile_elems, pt.max_elems);
+        plan.max_tile_segments = std::max(plan.max_tile_segments, pt.max_segs);
+        sum_blocks += pt.sum_blocks;
     }
     // Staging pays when footprints are compact runs; otherwise the gather kernel is used.
     const double avg_seg = plan.segs.empty() ? 0.0
