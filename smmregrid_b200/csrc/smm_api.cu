@@ -172,8 +172,9 @@ int launch_staged_t(int lpr, int kpl, int nct, dim3 grid, size_t smem, cudaStrea
         return SMM_OK;                                                                            \
     }
 #define SMM_CASE(L_, K_) SMM_CASE_N(L_, K_, 256) SMM_CASE_N(L_, K_, 512)
-    SMM_CASE(1, 4) SMM_CASE(2, 4) SMM_CASE(4, 4) SMM_CASE(1, 8) SMM_CASE(2, 8)
-    SMM_CASE(1, 16) SMM_CASE(2, 16) SMM_CASE(4, 16) SMM_CASE(8, 16) SMM_CASE(16, 16) SMM_CASE(32, 16)
+    SMM_CASE(1, 4) SMM_CASE(2, 4) SMM_CASE(1, 8) SMM_CASE(1, 12) SMM_CASE(1, 16) SMM_CASE(2, 12)
+    SMM_CASE(2, 14) SMM_CASE(2, 16) SMM_CASE(4, 12) SMM_CASE(4, 16) SMM_CASE(8, 12) SMM_CASE(8, 14)
+    SMM_CASE(8, 16) SMM_CASE(16, 16) SMM_CASE(32, 16)
 #undef SMM_CASE
 #undef SMM_CASE_N
     return fail(SMM_ERR_INVALID, "no staged kernel for this lane configuration");
@@ -254,10 +255,10 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
 
     ApplyArgs a{};
     a.B = B; a.x_bstride = xbs; a.y_bstride = ybs; a.remap_area_min = area_min;
-    {   // profiling aid: SMM_DEBUG_STREAM_ONLY=1 makes the staged consumers skip the arithmetic
-        const char *e = std::getenv("SMM_DEBUG_STREAM_ONLY");
-        a.debug_flags = (e && e[0] == '1') ? 1u : 0u;
-    }
+    // experiment switches are read once per process, not per launch
+    static const uint32_t k_debug_flags = env_int("SMM_DEBUG_STREAM_ONLY", 0) == 1 ? 1u : 0u;
+    static const int k_max_stages = std::max(2, env_int("SMM_MAX_STAGES", kMaxStages));
+    a.debug_flags = k_debug_flags;   // bit 0: staged consumers skip the arithmetic (profiling aid)
 
     auto fill_job = [&](const JobSpec &s, LevelJob &j) {
         const LevelDev &L = h->levels[s.level];
@@ -291,7 +292,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         size_t S = (nct == 256 && half > stage_off) ? (half - stage_off) / stage_bytes : 0;
         if (S < 3) S = (h->smem_optin - stage_off) / stage_bytes;        // one CTA per SM
         S = std::min<size_t>(S, kMaxStages);
-        S = std::min<size_t>(S, static_cast<size_t>(std::max(2, env_int("SMM_MAX_STAGES", kMaxStages))));
+        S = std::min<size_t>(S, static_cast<size_t>(k_max_stages));
         if (S < 2) return fail(SMM_ERR_INVALID, "internal: staged footprint does not fit");
         a.nstages = static_cast<int32_t>(S);
         a.stage_bytes = static_cast<uint32_t>(stage_bytes);

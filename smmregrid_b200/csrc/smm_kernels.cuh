@@ -164,20 +164,17 @@ __device__ __forceinline__ uint32_t pin_reg(uint32_t v)
 template <typename TX, int KPL, bool kFill>
 __device__ __forceinline__ double lane_sum(uint32_t sb, const uint32_t (&off)[KPL], const double (&w)[KPL])
 {
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    static_assert(KPL % 2 == 0, "links per lane come in pairs");
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int k = 0; k < KPL; k += 4) {
+    for (int k = 0; k < KPL; k += 2) {
         TX v0 = lds<TX>(sb + off[k + 0]);
         TX v1 = lds<TX>(sb + off[k + 1]);
-        TX v2 = lds<TX>(sb + off[k + 2]);
-        TX v3 = lds<TX>(sb + off[k + 3]);
-        if (kFill) { v0 = fill_invalid(v0); v1 = fill_invalid(v1); v2 = fill_invalid(v2); v3 = fill_invalid(v3); }
-        acc0 = fma(static_cast<double>(v0), w[k + 0], acc0);
-        acc1 = fma(static_cast<double>(v1), w[k + 1], acc1);
-        acc2 = fma(static_cast<double>(v2), w[k + 2], acc2);
-        acc3 = fma(static_cast<double>(v3), w[k + 3], acc3);
+        if (kFill) { v0 = fill_invalid(v0); v1 = fill_invalid(v1); }
+        acc[k % 4 + 0] = fma(static_cast<double>(v0), w[k + 0], acc[k % 4 + 0]);
+        acc[k % 4 + 1] = fma(static_cast<double>(v1), w[k + 1], acc[k % 4 + 1]);
     }
-    return (acc0 + acc1) + (acc2 + acc3);
+    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
 __device__ __forceinline__ bool not_finite(double v) { return !(fabs(v) <= 1.7976931348623157e+308); }

@@ -97,11 +97,19 @@ bool choose_lanes(int32_t m, int32_t &lpr, int32_t &kpl)
         int a = 0, b = 0;
         if (std::sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0 && m <= a * b) { lpr = a; kpl = b; return true; }
     }
+    // (lanes per row, links per lane): fewest padded slots first -- every slot, padded or not,
+    // costs an F2F conversion, and conversion throughput bounds link-dense operators
     if (m <= 4) { lpr = 1; kpl = 4; }
-    else if (m <= 8) { lpr = 2; kpl = 4; }
+    else if (m <= 8) { lpr = 1; kpl = 8; }
+    else if (m <= 12) { lpr = 1; kpl = 12; }
     else if (m <= 16) { lpr = 1; kpl = 16; }
+    else if (m <= 24) { lpr = 2; kpl = 12; }
+    else if (m <= 28) { lpr = 2; kpl = 14; }
     else if (m <= 32) { lpr = 2; kpl = 16; }
+    else if (m <= 48) { lpr = 4; kpl = 12; }
     else if (m <= 64) { lpr = 4; kpl = 16; }
+    else if (m <= 96) { lpr = 8; kpl = 12; }
+    else if (m <= 112) { lpr = 8; kpl = 14; }
     else if (m <= 128) { lpr = 8; kpl = 16; }
     else if (m <= 256) { lpr = 16; kpl = 16; }
     else if (m <= 512) { lpr = 32; kpl = 16; }

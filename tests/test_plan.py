@@ -106,7 +106,7 @@ def test_plan_emulation_matches_oracle(smm_lib, oracle, nnz_per_row):
 
 def test_plan_named_configs(smm_lib, oracle):
     from smmregrid_b200 import synth
-    for cfg, scale, lanes in (("C1", 1, (1, 4)), ("C2", 4, (2, 16)), ("C4", 5, (8, 16))):
+    for cfg, scale, lanes in (("C1", 1, (1, 4)), ("C2", 4, (2, 14)), ("C4", 5, (8, 14))):
         w = synth.config_weights(cfg, scale)
         n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
         p = HostPlan(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
