@@ -4,11 +4,11 @@ Public names mirror ``smmregrid/__init__.py`` for the part of the API on the hot
 """
 from .regrid import Regridder, regrid
 from .weights import (CdoWeights, WeightsMatrix, check_mask, compute_weights_matrix,
-                      compute_weights_matrix3d, mask_tensordot, mask_weights)
+                      compute_weights_matrix3d, enable_operator_cache, mask_tensordot, mask_weights)
 
 __version__ = "0.1.0"
 
 __all__ = [
     "Regridder", "regrid", "CdoWeights", "WeightsMatrix", "compute_weights_matrix",
-    "compute_weights_matrix3d", "mask_tensordot", "mask_weights", "check_mask",
+    "compute_weights_matrix3d", "mask_tensordot", "mask_weights", "check_mask", "enable_operator_cache",
 ]

@@ -107,12 +107,17 @@ __device__ __noinline__ double replay_row(const int32_t *__restrict__ rowptr,
 
 __device__ __forceinline__ bool near_threshold(double acc) { return fabs(acc - 1e19) <= 1e10; }
 
-template <typename TY>
-__device__ __forceinline__ TY finish(double acc, bool dead)
+// Epilogue of one destination value (regrid.py:553-570): imask / frac (folded into `dead`), then
+// `> 1e19 -> NaN`.  One comparison keeps ordinary values on the short path; only sums in the
+// neighbourhood of the threshold are replayed in the reference's summation order (`replay()`).
+template <typename TY, typename Replay>
+__device__ __forceinline__ TY finish(double acc, bool dead, Replay replay)
 {
-    // regrid.py:553-570: imask / frac (folded into `dead`) then `> 1e19 -> NaN`.
-    const double out = (dead || acc > 1e19) ? CUDART_NAN : acc;
-    return static_cast<TY>(out);
+    if (acc > 9.9e18) {
+        if (near_threshold(acc)) acc = replay();
+        if (acc > 1e19) acc = CUDART_NAN;
+    }
+    return static_cast<TY>(dead ? CUDART_NAN : acc);
 }
 
 __device__ __forceinline__ const LevelJob &find_job(const JobBatch &jb, int item, int &j)
@@ -291,13 +296,13 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
             if (job.masked && job.imask[row] == 0) dead = true;
             if (a.remap_area_min > 0.0 && job.frac[row] < a.remap_area_min) dead = true;
         }
-        TY *yrow = static_cast<TY *>(job.y) + row;
-        const TX *xbase = static_cast<const TX *>(job.x);
+        TY *yp = static_cast<TY *>(job.y) + row + b0 * a.y_bstride;      // this row's output, batch row b
+        const TX *xp = static_cast<const TX *>(job.x) + b0 * a.x_bstride;    // source row b (replay only)
         const bool stream_only = (a.debug_flags & 1u) != 0;
 
         int s = 0;
         uint32_t ph = 0;
-        for (int64_t b = b0; b < b1; ++b) {
+        for (int64_t b = b0; b < b1; ++b, yp += a.y_bstride, xp += a.x_bstride) {
             mbar_wait(full_addr + 8 * s, ph);
             const uint32_t sb = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
             double acc = 0.0;
@@ -310,11 +315,8 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_addr + 8 * s);   // stage may be refilled
             acc = group_sum<LPR>(acc);
-            if (l_in == 0 && valid) {
-                if (near_threshold(acc))
-                    acc = replay_row<TX>(job.rowptr, job.col, job.val, row, xbase + b * a.x_bstride);
-                yrow[b * a.y_bstride] = finish<TY>(acc, dead);
-            }
+            if (l_in == 0 && valid)
+                *yp = finish<TY>(acc, dead, [&]() { return replay_row<TX>(job.rowptr, job.col, job.val, row, xp); });
             if (++s == S) { s = 0; ph ^= 1u; }
         }
     }
@@ -381,11 +383,10 @@ gather_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         if (l_in == 0 && valid) {
 #pragma unroll
             for (int t = 0; t < BT; ++t) {
-                if (b + t < b1) {
-                    double r = acc[t];
-                    if (near_threshold(r)) r = replay_row<TX>(job.rowptr, job.col, job.val, row, xr[t]);
-                    yrow[(b + t) * a.y_bstride] = finish<TY>(r, dead);
-                }
+                if (b + t < b1)
+                    yrow[(b + t) * a.y_bstride] = finish<TY>(acc[t], dead, [&]() {
+                        return replay_row<TX>(job.rowptr, job.col, job.val, row, xr[t]);
+                    });
             }
         }
     }

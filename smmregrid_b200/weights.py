@@ -210,6 +210,56 @@ def _as_matrix_level(matrix):
     raise TypeError("expected a WeightsMatrix (or a level of one)")
 
 
+# ------------------------------------------------------------------ operator cache (opt-in)
+#
+# The reference rebuilds its sparse matrix per Regridder; building the device operator costs
+# 0.5-2 s for multi-million-link weight sets, so callers that create many Regridders from the
+# same weights (one per variable / file) can share it.  Keyed by a content hash of the link
+# arrays, bounded, process-local; the epilogue vectors (dst_grid_imask / dst_grid_frac) belong
+# to the handle, so a cached operator is only reused for identical masks as well.
+
+_CACHE = {}
+_CACHE_MAX = 0
+
+
+def enable_operator_cache(max_entries: int = 4):
+    """Keep up to ``max_entries`` device operators alive for reuse (0 disables and clears)."""
+    global _CACHE_MAX
+    _CACHE_MAX = int(max_entries)
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.pop(next(iter(_CACHE)))
+
+
+def _content_key(w: "CdoWeights", device, names):
+    import hashlib
+    h = hashlib.sha1()
+    h.update(repr((device, w.sizes["src_grid_size"], w.sizes["dst_grid_size"])).encode())
+    for name in names:
+        a = w.vars.get(name)
+        if a is not None:
+            a = np.ascontiguousarray(a)
+            h.update(name.encode() + str(a.dtype).encode() + str(a.shape).encode())
+            h.update(a.view(np.uint8).reshape(-1).data)
+    return h.hexdigest()
+
+
+def _cached(w, device, names, build):
+    if _CACHE_MAX <= 0:
+        return build()
+    key = _content_key(w, device, names)
+    wm = _CACHE.pop(key, None)
+    if wm is None or not wm._h:
+        wm = build()
+    _CACHE[key] = wm                       # most recently used last
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.pop(next(iter(_CACHE)))
+    return wm
+
+
+_KEY_VARS = ("src_address", "dst_address", "remap_matrix", "link_length", "dst_grid_imask", "dst_grid_frac",
+             "src_grid_imask")
+
+
 def compute_weights_matrix(weights, device=None) -> WeightsMatrix:
     """Convert CDO weights to a device operator (reference: ``weights.py:25-44``).
 
@@ -225,12 +275,16 @@ def compute_weights_matrix(weights, device=None) -> WeightsMatrix:
         raise ValueError("src_address, dst_address and remap_matrix disagree on the number of links")
     n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
     dev = _device_index(device)
-    h = ctypes.c_void_p()
-    _lib.check(_lib.load().smm_create(n_src, n_dst, src.size, _ptr(src), _ptr(dst), _ptr(rm),
-                                     num_wgts, 1, dev, ctypes.byref(h)))
-    wm = WeightsMatrix(h, 1, dev, n_src, n_dst)
-    _install_masks(wm, w)
-    return wm
+
+    def build():
+        h = ctypes.c_void_p()
+        _lib.check(_lib.load().smm_create(n_src, n_dst, src.size, _ptr(src), _ptr(dst), _ptr(rm),
+                                         num_wgts, 1, dev, ctypes.byref(h)))
+        wm = WeightsMatrix(h, 1, dev, n_src, n_dst)
+        _install_masks(wm, w)
+        return wm
+
+    return _cached(w, dev, _KEY_VARS, build)
 
 
 def compute_weights_matrix3d(weights, mask_dim="lev", device=None) -> WeightsMatrix:
@@ -246,12 +300,16 @@ def compute_weights_matrix3d(weights, mask_dim="lev", device=None) -> WeightsMat
     num_wgts = rm.shape[2]
     n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
     dev = _device_index(device)
-    h = ctypes.c_void_p()
-    _lib.check(_lib.load().smm_create_levels(L, _ptr(ll), nl_max, n_src, n_dst, _ptr(src), _ptr(dst),
-                                            _ptr(rm), num_wgts, 1, dev, ctypes.byref(h)))
-    wm = WeightsMatrix(h, L, dev, n_src, n_dst)
-    _install_masks(wm, w)
-    return wm
+
+    def build():
+        h = ctypes.c_void_p()
+        _lib.check(_lib.load().smm_create_levels(L, _ptr(ll), nl_max, n_src, n_dst, _ptr(src), _ptr(dst),
+                                                _ptr(rm), num_wgts, 1, dev, ctypes.byref(h)))
+        wm = WeightsMatrix(h, L, dev, n_src, n_dst)
+        _install_masks(wm, w)
+        return wm
+
+    return _cached(w, dev, _KEY_VARS, build)
 
 
 def _install_masks(wm: WeightsMatrix, w: CdoWeights):

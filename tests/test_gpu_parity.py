@@ -394,3 +394,22 @@ def test_c2_full_size_properties(smm_lib, cuda):
     rg.weights_matrix.set_kernel("gather")
     yg = rg.regrid(x).reshape(B, 180, 360)
     assert torch.allclose(yg, y, rtol=1e-12, atol=0)
+
+
+def test_operator_cache_reuses_handle(smm_lib, cuda):
+    import smmregrid_b200 as sb
+    from smmregrid_b200 import synth
+    w = synth.config_weights("C1")
+    sb.enable_operator_cache(2)
+    try:
+        a = sb.Regridder(weights=w)
+        b = sb.Regridder(weights=synth.config_weights("C1"))          # same content, new object
+        assert a.weights_matrix is b.weights_matrix
+        c = sb.Regridder(weights=synth.config_weights("C2", 8))
+        assert c.weights_matrix is not a.weights_matrix
+        x = synth.synthetic_field((2, a.n_src), np.float32)
+        assert np.array_equal(a.regrid(x), b.regrid(x), equal_nan=True)
+    finally:
+        sb.enable_operator_cache(0)
+    d = sb.Regridder(weights=w)
+    assert d.weights_matrix is not a.weights_matrix
