@@ -252,6 +252,9 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         // row; producer p issues segments p, p + 4, ... (one per lane)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
         const int p = warp - kConsumerWarps;
+        // small footprints need fewer issuing warps (<= 3 copies each); the others retire at once
+        const int active = td.nseg >= 3 * kProducerWarps ? kProducerWarps : (td.nseg + 2) / 3 > 0 ? (td.nseg + 2) / 3 : 1;
+        if (p >= active) return;
         const uint64_t policy = l2_evict_first_policy();
         const char *xbase = static_cast<const char *>(job.x);
         const uint32_t tile_bytes = static_cast<uint32_t>(td.elems) * sizeof(TX);
@@ -265,7 +268,7 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
             if (p == 0 && lane == 0) mbar_arrive_expect_tx(fb, tile_bytes);
             const char *xrow = xbase + b * a.x_bstride * static_cast<int64_t>(sizeof(TX));
             const uint32_t sbase = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
-            for (int i = p + kProducerWarps * lane; i < td.nseg; i += 32 * kProducerWarps) {
+            for (int i = p + active * lane; i < td.nseg; i += 32 * active) {
                 const SegB e = ssegs[i];
                 tma_bulk_g2s(sbase + e.dst, xrow + e.src, e.len, fb, policy);
             }
