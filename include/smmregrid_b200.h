@@ -186,6 +186,19 @@ void smm_host_plan_free(smm_host_plan *p);
  * SMM_KERNEL_STAGED (fails if the level has no staged plan) or SMM_KERNEL_GATHER. */
 int smm_set_kernel(smm_handle *h, int32_t kernel);
 
+/*
+ * EXTENSION, off by default (the reference has no counterpart; its README notes that fields
+ * with time-varying missing points are not handled, README.md:40).  With
+ * min_valid_fraction >= 0 subsequent applies EXCLUDE non-finite source values instead of
+ * filling them with 1e20: a destination whose links see missing sources becomes
+ *   sum_valid(w*x) * sum_all(w) / sum_valid(w)   if |sum_valid(w)| >= min_valid_fraction*|sum_all(w)|
+ *   NaN                                          otherwise,
+ * destinations without missing sources are unchanged, dst_grid_imask / dst_grid_frac masking
+ * still applies and the `> 1e19 -> NaN` rule is not used.  A negative value restores the
+ * reference semantics.
+ */
+int smm_set_renormalize(smm_handle *h, double min_valid_fraction);
+
 /* Kernels launched by this library in the calling process so far (bench.py gpu_launches). */
 int64_t smm_launch_count(void);
 

@@ -254,3 +254,29 @@ def regrid3d_np(x, level_axis, data_levels, weight_levels, mats, dst_imask, dst_
         outs.append(apply(xa, mats[widx], dst_imask[widx], fr, remap_area_min, bool(masked[widx])))
     y = np.stack(outs, axis=0)
     return np.moveaxis(y, 0, -2)
+
+
+def apply_weights_renorm_np(x, mat: CooMatrix, dst_imask=None, dst_frac=None, remap_area_min=0.5,
+                            masked=True, min_valid=0.5):
+    """Checker for the opt-in renormalising EXTENSION (not reference behaviour): non-finite
+    sources are excluded; a destination that saw missing sources becomes
+    sum_valid(w x) * sum_all(w) / sum_valid(w), or NaN when |sum_valid(w)| < min_valid*|sum_all(w)|;
+    destinations without missing sources keep the plain sum."""
+    import scipy.sparse as sp
+    x = np.asarray(x)
+    kept = x.shape[:-1]
+    xa = x.reshape(-1, x.shape[-1]).astype(np.float64)
+    fin = np.isfinite(xa)
+    W = sp.csr_matrix((mat.w, (mat.src, mat.dst)), shape=mat.shape).T.tocsr()
+    wx = np.asarray((W @ np.where(fin, xa, 0.0).T).T)
+    wv = np.asarray((W @ fin.astype(np.float64).T).T)
+    wa = np.asarray(W @ np.ones(mat.shape[0]))[None, :]
+    missing = np.asarray((abs(W) @ (~fin).astype(np.float64).T).T) > 0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ren = np.where((np.abs(wv) >= min_valid * np.abs(wa)) & (wv != 0), wx * (wa / wv), np.nan)
+    y = np.where(missing, ren, wx)
+    if masked:
+        y = np.where(np.asarray(dst_imask).reshape(1, -1).astype(bool), y, np.nan)
+    if remap_area_min > 0.0:
+        y = np.where(np.broadcast_to(dst_frac, y.shape) < remap_area_min, np.nan, y)
+    return y.reshape(kept + (mat.shape[1],))

@@ -53,6 +53,7 @@ SIGNATURES = {
     "smm_host_plan_rowmap": (ctypes.c_int, [vp, vp]),
     "smm_host_plan_free": (None, [vp]),
     "smm_set_kernel": (ctypes.c_int, [vp, i32]),
+    "smm_set_renormalize": (ctypes.c_int, [vp, f64]),
     "smm_launch_count": (i64, []),
     "smm_last_error": (ctypes.c_char_p, []),
     "smm_version": (ctypes.c_char_p, []),

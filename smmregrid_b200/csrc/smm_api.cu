@@ -73,6 +73,7 @@ struct smm_handle {
     int sm_count = 148;
     size_t smem_optin = 0;
     int force_kernel = 0;
+    double renorm_min_valid = -1.0;      // opt-in extension, see smm_set_renormalize
     std::vector<LevelDev> levels;
     std::mutex host_mu;
     HostSlot slots[3];
@@ -255,6 +256,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
 
     ApplyArgs a{};
     a.B = B; a.x_bstride = xbs; a.y_bstride = ybs; a.remap_area_min = area_min;
+    a.renorm_min_valid = h->renorm_min_valid;
     // experiment switches are read once per process, not per launch
     static const uint32_t k_debug_flags = env_int("SMM_DEBUG_STREAM_ONLY", 0) == 1 ? 1u : 0u;
     static const int k_max_stages = std::max(2, env_int("SMM_MAX_STAGES", kMaxStages));
@@ -849,6 +851,15 @@ int smm_set_kernel(smm_handle *h, int32_t kernel)
     if (kernel != 0 && kernel != SMM_KERNEL_STAGED && kernel != SMM_KERNEL_GATHER)
         return fail(SMM_ERR_INVALID, "kernel must be 0, SMM_KERNEL_STAGED or SMM_KERNEL_GATHER");
     h->force_kernel = kernel;
+    return SMM_OK;
+}
+
+int smm_set_renormalize(smm_handle *h, double min_valid_fraction)
+{
+    if (!h) return fail(SMM_ERR_INVALID, "null handle");
+    if (!(min_valid_fraction < 0.0) && !(min_valid_fraction <= 1.0))
+        return fail(SMM_ERR_INVALID, "min_valid_fraction must be negative (off) or within [0, 1]");
+    h->renorm_min_valid = min_valid_fraction < 0.0 ? -1.0 : min_valid_fraction;
     return SMM_OK;
 }
 

@@ -75,6 +75,7 @@ struct ApplyArgs {
     uint32_t stage_bytes; // bytes reserved per stage (>= largest footprint, 128-aligned)
     uint32_t stage_off;   // byte offset of stage 0 in dynamic shared memory
     double remap_area_min;
+    double renorm_min_valid;  // < 0: reference semantics (fill 1e20); >= 0: opt-in renormalising mode
     uint32_t debug_flags; // bit 0: stream only (profiling aid: consumers skip the arithmetic)
 };
 

@@ -182,6 +182,36 @@ __device__ __forceinline__ double lane_sum(uint32_t sb, const uint32_t (&off)[KP
     return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
+// Opt-in renormalising mode (extension, off by default): the sums a lane needs to
+// EXCLUDE non-finite sources instead of filling them: sum of w*x over finite x, sum of w over
+// finite x, sum of all w.
+// Kept out of line and fed from the plan arrays (not from the caller's register image) so that
+// this cold path costs the hot loop no registers.
+template <typename TX, int KPL, int NCT>
+__device__ __noinline__ void lane_sum_valid(const double *__restrict__ wplan, const uint16_t *__restrict__ iplan,
+                                            size_t base, uint32_t sb, double *out3)
+{
+    double wx = 0.0, wv = 0.0, wa = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < KPL; ++k) {
+        const double wk = __ldg(wplan + base + static_cast<size_t>(k) * NCT);
+        const uint32_t o = static_cast<uint32_t>(__ldg(iplan + base + static_cast<size_t>(k) * NCT)) *
+                           static_cast<uint32_t>(sizeof(TX));
+        const TX v = lds<TX>(sb + o);
+        wa += wk;
+        if (fill_invalid(v) == v) { wx = fma(static_cast<double>(v), wk, wx); wv += wk; }   // false for NaN, +-inf
+    }
+    out3[0] = wx; out3[1] = wv; out3[2] = wa;
+}
+
+// renormalised value of a row from its group-reduced sums; NaN below the valid-weight threshold
+__device__ __forceinline__ double renormalise(double wx, double wv, double wa, double min_valid)
+{
+    if (wv == wa) return wx;                           // nothing was missing (also rows without links)
+    if (!(fabs(wv) >= min_valid * fabs(wa)) || wv == 0.0) return CUDART_NAN;
+    return wx * (wa / wv);
+}
+
 __device__ __forceinline__ bool not_finite(double v) { return !(fabs(v) <= 1.7976931348623157e+308); }
 
 // CTA roles: NCT/32 consumer warps (two warpgroups for NCT = 256) | one warpgroup of 4 TMA
@@ -309,17 +339,37 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
             mbar_wait(full_addr + 8 * s, ph);
             const uint32_t sb = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
             double acc = 0.0;
+            bool renormed = false;
             if (!stream_only) {
                 // fast path: raw values.  A non-finite partial means some source value was NaN/inf
-                // (regrid.py:545-547 fills those with 1e20): redo the warp's links with the fill.
+                // (regrid.py:545-547 fills those with 1e20): redo the warp's links with the fill --
+                // or, in the opt-in renormalising mode, without the missing sources.
                 acc = lane_sum<TX, KPL, false>(sb, off, w);
-                if (__any_sync(0xffffffffu, not_finite(acc))) acc = lane_sum<TX, KPL, true>(sb, off, w);
+                if (__any_sync(0xffffffffu, not_finite(acc))) {
+                    if (a.renorm_min_valid < 0.0) {
+                        acc = lane_sum<TX, KPL, true>(sb, off, w);
+                    } else {
+                        double s3[3];
+                        lane_sum_valid<TX, KPL, NCT>(job.wplan, job.iplan, static_cast<size_t>(tile) * KPL * NCT + tid, sb, s3);
+                        acc = renormalise(group_sum<LPR>(s3[0]), group_sum<LPR>(s3[1]), group_sum<LPR>(s3[2]),
+                                          a.renorm_min_valid);
+                        renormed = true;
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(empty_addr + 8 * s);   // stage may be refilled
-            acc = group_sum<LPR>(acc);
-            if (l_in == 0 && valid)
-                *yp = finish<TY>(acc, dead, [&]() { return replay_row<TX>(job.rowptr, job.col, job.val, row, xp); });
+            if (renormed) {
+                if (l_in == 0 && valid) *yp = static_cast<TY>(dead ? CUDART_NAN : acc);
+            } else {
+                acc = group_sum<LPR>(acc);
+                if (l_in == 0 && valid) {
+                    if (a.renorm_min_valid < 0.0)
+                        *yp = finish<TY>(acc, dead, [&]() { return replay_row<TX>(job.rowptr, job.col, job.val, row, xp); });
+                    else
+                        *yp = static_cast<TY>(dead ? CUDART_NAN : acc);      // no fill, so no 1e19 rule
+                }
+            }
             if (++s == S) { s = 0; ph ^= 1u; }
         }
     }
@@ -357,6 +407,7 @@ gather_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
     }
     const TX *xbase = static_cast<const TX *>(job.x);
     TY *yrow = static_cast<TY *>(job.y) + row;
+    const bool do_fill = a.renorm_min_valid < 0.0;
 
     for (int64_t b = b0; b < b1; b += BT) {
         const TX *xr[BT];
@@ -375,13 +426,36 @@ gather_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
 #pragma unroll
             for (int t = 0; t < BT; ++t) v[t] = ld_nc(xr[t] + c);
 #pragma unroll
-            for (int t = 0; t < BT; ++t)
-                acc[t] = fma(static_cast<double>(fill_invalid(v[t])), wv, acc[t]);
+            for (int t = 0; t < BT; ++t)   // renormalising mode keeps raw values: a non-finite sum flags the row
+                acc[t] = fma(static_cast<double>(do_fill ? fill_invalid(v[t]) : v[t]), wv, acc[t]);
         }
 #pragma unroll
         for (int t = 0; t < BT; ++t) {
 #pragma unroll
             for (int o = LPR / 2; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+        }
+        if (a.renorm_min_valid >= 0.0) {
+            // opt-in renormalising mode: rows whose plain sum is non-finite are redone without the
+            // missing sources (sequentially by the row's first lane: rare rows, simple code)
+            if (l_in == 0 && valid) {
+#pragma unroll
+                for (int t = 0; t < BT; ++t) {
+                    if (b + t >= b1) continue;
+                    double r = acc[t];
+                    if (not_finite(r)) {
+                        double wx = 0.0, wv = 0.0, wa = 0.0;
+                        for (int j = j0; j < j1; ++j) {
+                            const TX v = xr[t][job.col[j]];
+                            const double wj = job.val[j];
+                            wa += wj;
+                            if (fill_invalid(v) == v) { wx = fma(static_cast<double>(v), wj, wx); wv += wj; }
+                        }
+                        r = renormalise(wx, wv, wa, a.renorm_min_valid);
+                    }
+                    yrow[(b + t) * a.y_bstride] = static_cast<TY>(dead ? CUDART_NAN : r);
+                }
+            }
+            continue;
         }
         if (l_in == 0 && valid) {
 #pragma unroll

@@ -67,7 +67,7 @@ class Regridder(object):
                  method='con', remap_area_min=DEFAULT_AREA_MIN, transpose=True, mask_dim=None,
                  vertical_dim=None, horizontal_dims=None, cdo_extra=None, cdo_options=None,
                  check_nan=False, cdo='cdo', loglevel='WARNING',
-                 device=None, out_dtype=None):
+                 device=None, out_dtype=None, renormalize=None):
         if (source_grid is None or target_grid is None) and (weights is None):
             raise ValueError("Either weights or source_grid/target_grid must be supplied")
         if vertical_dim is not None and mask_dim is None:      # deprecated alias (regrid.py:107)
@@ -103,6 +103,9 @@ class Regridder(object):
             w = mask_weights(w, self.weights_matrix, self.mask_dim)
             self.masked = check_mask(w, self.mask_dim)
         self.weights = w
+        # extension beyond the reference (off by default): time-varying missing values are
+        # excluded and the remaining weights renormalised, NaN below `renormalize` valid fraction
+        self.renormalize = renormalize
         n = w.sizes
         self.n_src, self.n_dst = n["src_grid_size"], n["dst_grid_size"]
         self.src_grid_shape = tuple(int(v) for v in np.atleast_1d(w["src_grid_dims"]))[::-1] \
@@ -129,6 +132,17 @@ class Regridder(object):
             return self.regrid_array(source_data)
         if isinstance(source_data, np.ndarray) or _is_tensor(source_data):
             return self.regrid_array(source_data, level_axis=level_axis, levels=levels)
+        if isinstance(source_data, dict):
+            # plain-array counterpart of Dataset.map (regrid.py:262): one entry per variable;
+            # bounds variables are dropped except time bounds (regrid.py:482-490)
+            out = {}
+            for name, arr in source_data.items():
+                if any(sub in str(name) for sub in ("bnds", "bounds", "vertices")):
+                    if 'time' in str(name):
+                        out[name] = arr
+                    continue
+                out[name] = self.regrid_array(arr, level_axis=level_axis, levels=levels)
+            return out
         raise TypeError('The object provided is not a Xarray object!')
 
     def regrid_array(self, source_data, level_axis=None, levels=None):
@@ -165,6 +179,7 @@ class Regridder(object):
         if len(levels) != Ld:
             raise ValueError("levels must have one value per data level")
         widx = np.array([select_level(wl, lev, self.mask_dim) for lev in levels], dtype=np.int32)
+        self.weights_matrix.set_renormalize(self.renormalize)
         masked = np.ascontiguousarray(np.asarray(self.masked)[widx], dtype=np.uint8)
 
         was_numpy = isinstance(source_data, np.ndarray)
@@ -234,6 +249,7 @@ class Regridder(object):
         B = int(np.prod(kept_shape)) if kept_shape else 1
         lib = _lib.load()
         masked = 1 if bool(masked) else 0
+        parent.set_renormalize(self.renormalize)
 
         if isinstance(source_data, np.ndarray) or not source_data.is_cuda:
             # host data: chunked H2D -> kernel -> D2H pipeline inside the library

@@ -191,6 +191,12 @@ class WeightsMatrix:
                 raise ValueError(f"expected {self.shape[1]} destination cells, got {a.size}")
         _lib.check(_lib.load().smm_set_dst_mask(self.handle, level, _ptr(im), _ptr(fr)))
 
+    def set_renormalize(self, min_valid_fraction: Optional[float]):
+        """Opt-in extension (off by default): exclude non-finite sources and renormalise the
+        remaining weights; ``None`` restores the reference's fill-with-1e20 semantics."""
+        v = -1.0 if min_valid_fraction is None else float(min_valid_fraction)
+        _lib.check(_lib.load().smm_set_renormalize(self.handle, v))
+
     def set_kernel(self, kernel: Optional[str]):
         code = {None: 0, "auto": 0, "staged": _lib.SMM_KERNEL_STAGED, "gather": _lib.SMM_KERNEL_GATHER}[kernel]
         _lib.check(_lib.load().smm_set_kernel(self.handle, code))

@@ -413,3 +413,85 @@ def test_operator_cache_reuses_handle(smm_lib, cuda):
         sb.enable_operator_cache(0)
     d = sb.Regridder(weights=w)
     assert d.weights_matrix is not a.weights_matrix
+
+
+def test_concurrent_applies_on_streams(smm_lib, oracle, cuda):
+    """The header promises smm_apply is re-entrant across host threads and streams: four
+    threads, each on its own stream, hammer one handle; every result must be exact."""
+    import threading
+    import torch
+    from smmregrid_b200 import _lib, synth
+    w = synth.config_weights("C2", 4)
+    n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+    mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    h = _create(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    fr = np.ascontiguousarray(w["dst_grid_frac"], np.float64)
+    _lib.check(smm_lib.smm_set_dst_mask(h, 0, None, fr.ctypes.data))
+    errors = []
+
+    def worker(seed):
+        try:
+            B = 17 + seed
+            x = synth.synthetic_field((B, n_src), np.float32, seed=seed, nan_mode="random")
+            y_ref = oracle.apply_weights_c(x, mat, None, fr, 0.5, False)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                xd = torch.from_numpy(x).cuda()
+                for _ in range(20):
+                    yd = torch.empty((B, n_dst), dtype=torch.float64, device="cuda")
+                    _lib.check(smm_lib.smm_apply(h, 0, xd.data_ptr(), 0, B, n_src, yd.data_ptr(), 1, n_dst, 0, 0.5,
+                                                 st.cuda_stream))
+                st.synchronize()
+                assert_parity(yd.cpu().numpy(), y_ref, RTOL_F64, f"thread {seed}")
+        except Exception as e:          # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(s,)) for s in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    smm_lib.smm_destroy(h)
+    assert not errors, errors
+
+
+def test_dict_of_variables(smm_lib, cuda):
+    from smmregrid_b200 import Regridder, synth
+    rg = Regridder(weights=synth.config_weights("C1"))
+    x = synth.synthetic_field((3, 73, 144), np.float32)
+    out = rg.regrid({"tas": x, "pr": 2 * x, "lat_bnds": np.zeros((73, 2)), "time_bnds": np.zeros((3, 2))})
+    assert set(out) == {"tas", "pr", "time_bnds"}
+    assert out["tas"].shape == (3, 90, 180) and np.allclose(out["pr"], 2 * out["tas"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("xdt", [np.float32, np.float64])
+def test_renormalising_extension(smm_lib, oracle, cuda, xdt):
+    """Opt-in extension (off by default): time-varying missing values are excluded and the
+    remaining weights renormalised.  Reference mode on the same handle must be unaffected."""
+    from smmregrid_b200 import Regridder, synth
+    w = synth.config_weights("C2", 4)
+    n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+    rng = np.random.default_rng(5)
+    B = 9
+    x = (280 + 20 * rng.standard_normal((B, n_src))).astype(xdt)
+    for b in range(B):                                   # a different blob of missing data per step
+        c = rng.integers(0, n_src)
+        x[b, max(0, c - 3000):c + 3000] = np.nan
+    x[0, rng.random(n_src) < 0.3] = np.nan
+    x[1, 5] = np.inf
+    mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    imask = np.ones(n_dst, np.int32)
+    for min_valid in (0.0, 0.5, 0.9):
+        ref = oracle.apply_weights_renorm_np(x, mat, imask, w["dst_grid_frac"], 0.5, False, min_valid)
+        rg = Regridder(weights=w, remap_area_min=0.5, renormalize=min_valid)
+        for kernel in (None, "gather"):
+            rg.weights_matrix.set_kernel(kernel)
+            y = rg.regrid(x).reshape(B, n_dst)
+            assert_parity(y, ref, 1e-12, f"renorm {min_valid} {kernel}")
+        # fewer NaNs than the reference semantics, and values stay in the data range
+        y_ref_mode = Regridder(weights=w, remap_area_min=0.5).regrid(x).reshape(B, n_dst)
+        assert np.isnan(y).sum() <= np.isnan(y_ref_mode).sum()
+        assert np.nanmax(y) < 400 and np.nanmin(y) > 150
+    # off again: bit-identical NaN pattern with the oracle's reference semantics
+    y0 = Regridder(weights=w, remap_area_min=0.5).regrid(x).reshape(B, n_dst)
+    assert_parity(y0, oracle.apply_weights_c(x, mat, None, w["dst_grid_frac"], 0.5, False), 1e-12, "reference mode")
