@@ -72,7 +72,9 @@ struct ApplyArgs {
     int64_t chunk;        // batch rows per work item
     int32_t nchunks;
     int32_t nstages;
-    uint32_t stage_bytes; // bytes reserved per stage (>= largest footprint, 128-aligned)
+    uint32_t stage_bytes; // bytes reserved per stage = rows_per_stage * row_bytes
+    uint32_t row_bytes;   // bytes one batch row's footprint occupies in a stage (>= largest footprint, 128-aligned)
+    int32_t rows_per_stage;   // batch rows staged together (small footprints: amortises barrier + loop overhead)
     uint32_t stage_off;   // byte offset of stage 0 in dynamic shared memory
     double remap_area_min;
     double renorm_min_valid;  // < 0: reference semantics (fill 1e20); >= 0: opt-in renormalising mode

@@ -283,24 +283,31 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
         const int p = warp - kConsumerWarps;
         // small footprints need fewer issuing warps (<= 3 copies each); the others retire at once
-        const int active = td.nseg >= 3 * kProducerWarps ? kProducerWarps : (td.nseg + 2) / 3 > 0 ? (td.nseg + 2) / 3 : 1;
+        const int per_stage = td.nseg * a.rows_per_stage;
+        const int active = per_stage >= 3 * kProducerWarps ? kProducerWarps : (per_stage + 2) / 3 > 0 ? (per_stage + 2) / 3 : 1;
         if (p >= active) return;
         const uint64_t policy = l2_evict_first_policy();
         const char *xbase = static_cast<const char *>(job.x);
         const uint32_t tile_bytes = static_cast<uint32_t>(td.elems) * sizeof(TX);
+        const int NB = a.rows_per_stage;
+        const int64_t xrow_stride = a.x_bstride * static_cast<int64_t>(sizeof(TX));
         int s = 0;
         uint32_t ph = 0;
-        for (int64_t b = b0; b < b1; ++b) {
+        for (int64_t g = b0; g < b1; g += NB) {          // one stage = up to NB consecutive batch rows
+            const int nb = (g + NB <= b1) ? NB : static_cast<int>(b1 - g);
             mbar_wait(empty_addr + 8 * s, ph ^ 1u);
             const uint32_t fb = full_addr + 8 * s;
             // the phase cannot complete before this arrive, so copies of the other producers that
             // land earlier only drive the transaction count transiently negative
-            if (p == 0 && lane == 0) mbar_arrive_expect_tx(fb, tile_bytes);
-            const char *xrow = xbase + b * a.x_bstride * static_cast<int64_t>(sizeof(TX));
+            if (p == 0 && lane == 0) mbar_arrive_expect_tx(fb, tile_bytes * static_cast<uint32_t>(nb));
+            const char *xg = xbase + g * xrow_stride;
             const uint32_t sbase = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
-            for (int i = p + active * lane; i < td.nseg; i += 32 * active) {
-                const SegB e = ssegs[i];
-                tma_bulk_g2s(sbase + e.dst, xrow + e.src, e.len, fb, policy);
+            const int ncopies = nb * td.nseg;
+            for (int i = p + active * lane; i < ncopies; i += 32 * active) {
+                const int n = i / td.nseg;
+                const SegB e = ssegs[i - n * td.nseg];
+                tma_bulk_g2s(sbase + static_cast<uint32_t>(n) * a.row_bytes + e.dst, xg + n * xrow_stride + e.src, e.len,
+                             fb, policy);
             }
             if (++s == S) { s = 0; ph ^= 1u; }
         }
@@ -333,41 +340,48 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         const TX *xp = static_cast<const TX *>(job.x) + b0 * a.x_bstride;    // source row b (replay only)
         const bool stream_only = (a.debug_flags & 1u) != 0;
 
+        const int NB = a.rows_per_stage;
         int s = 0;
         uint32_t ph = 0;
-        for (int64_t b = b0; b < b1; ++b, yp += a.y_bstride, xp += a.x_bstride) {
+        for (int64_t g = b0; g < b1; g += NB) {          // one stage = up to NB consecutive batch rows
+            const int nb = (g + NB <= b1) ? NB : static_cast<int>(b1 - g);
             mbar_wait(full_addr + 8 * s, ph);
-            const uint32_t sb = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
-            double acc = 0.0;
-            bool renormed = false;
-            if (!stream_only) {
-                // fast path: raw values.  A non-finite partial means some source value was NaN/inf
-                // (regrid.py:545-547 fills those with 1e20): redo the warp's links with the fill --
-                // or, in the opt-in renormalising mode, without the missing sources.
-                acc = lane_sum<TX, KPL, false>(sb, off, w);
-                if (__any_sync(0xffffffffu, not_finite(acc))) {
-                    if (a.renorm_min_valid < 0.0) {
-                        acc = lane_sum<TX, KPL, true>(sb, off, w);
-                    } else {
-                        double s3[3];
-                        lane_sum_valid<TX, KPL, NCT>(job.wplan, job.iplan, static_cast<size_t>(tile) * KPL * NCT + tid, sb, s3);
-                        acc = renormalise(group_sum<LPR>(s3[0]), group_sum<LPR>(s3[1]), group_sum<LPR>(s3[2]),
-                                          a.renorm_min_valid);
-                        renormed = true;
+            uint32_t sb = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
+#pragma unroll 1
+            for (int n = 0; n < nb; ++n, sb += a.row_bytes, yp += a.y_bstride, xp += a.x_bstride) {
+                double acc = 0.0;
+                bool renormed = false;
+                if (!stream_only) {
+                    // fast path: raw values.  A non-finite partial means some source value was NaN/inf
+                    // (regrid.py:545-547 fills those with 1e20): redo the warp's links with the fill --
+                    // or, in the opt-in renormalising mode, without the missing sources.
+                    acc = lane_sum<TX, KPL, false>(sb, off, w);
+                    if (__any_sync(0xffffffffu, not_finite(acc))) {
+                        if (a.renorm_min_valid < 0.0) {
+                            acc = lane_sum<TX, KPL, true>(sb, off, w);
+                        } else {
+                            double s3[3];
+                            lane_sum_valid<TX, KPL, NCT>(job.wplan, job.iplan, static_cast<size_t>(tile) * KPL * NCT + tid, sb, s3);
+                            acc = renormalise(group_sum<LPR>(s3[0]), group_sum<LPR>(s3[1]), group_sum<LPR>(s3[2]),
+                                              a.renorm_min_valid);
+                            renormed = true;
+                        }
                     }
                 }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty_addr + 8 * s);   // stage may be refilled
-            if (renormed) {
-                if (l_in == 0 && valid) *yp = static_cast<TY>(dead ? CUDART_NAN : acc);
-            } else {
-                acc = group_sum<LPR>(acc);
-                if (l_in == 0 && valid) {
-                    if (a.renorm_min_valid < 0.0)
-                        *yp = finish<TY>(acc, dead, [&]() { return replay_row<TX>(job.rowptr, job.col, job.val, row, xp); });
-                    else
-                        *yp = static_cast<TY>(dead ? CUDART_NAN : acc);      // no fill, so no 1e19 rule
+                if (n == nb - 1) {                           // last row read: the stage may be refilled
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty_addr + 8 * s);
+                }
+                if (renormed) {
+                    if (l_in == 0 && valid) *yp = static_cast<TY>(dead ? CUDART_NAN : acc);
+                } else {
+                    acc = group_sum<LPR>(acc);
+                    if (l_in == 0 && valid) {
+                        if (a.renorm_min_valid < 0.0)
+                            *yp = finish<TY>(acc, dead, [&]() { return replay_row<TX>(job.rowptr, job.col, job.val, row, xp); });
+                        else
+                            *yp = static_cast<TY>(dead ? CUDART_NAN : acc);      // no fill, so no 1e19 rule
+                    }
                 }
             }
             if (++s == S) { s = 0; ph ^= 1u; }
