@@ -1,12 +1,13 @@
 // smm_kernels.cuh -- sm_100a kernels of the weight-application path.
 //
-//   staged_kernel   Y = X.W for matrices whose tiles have a compact source footprint
+//   staged_kernel   Y = X.W for operators whose tiles have a compact source footprint
 //                   (structured / locally ordered sources).  Four producer warps stream the
-//                   tile's footprint of each batch row into shared memory with 1-D TMA bulk
-//                   copies (cp.async.bulk + mbarrier complete_tx, L2 evict-first); eight
-//                   consumer warps hold the tile's link weights and footprint offsets in
-//                   REGISTERS for the whole batch loop, so per batch row the only traffic
-//                   is the X stream itself.  LPR lanes share one destination row.
+//                   tile's footprint of up to 8 batch rows per stage into shared memory with
+//                   1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx, L2
+//                   evict-first); the consumer warps hold the tile's link weights and
+//                   footprint offsets in REGISTERS for the whole batch loop, so per batch row
+//                   the only HBM traffic is the X stream in and the tile's rows out.  LPR
+//                   lanes share one destination row.
 //   gather_kernel   generic CSR fallback: direct ld.global.nc gathers, kGatherBT batch rows
 //                   register-blocked per thread (scattered sources, oversized rows,
 //                   unaligned slabs).
@@ -14,9 +15,11 @@
 //
 // Numerics (smmregrid/regrid.py:544-570): non-finite x -> 1e20 in x's dtype, float64
 // products/accumulation, NaN where dst_grid_imask == 0 / dst_grid_frac < remap_area_min /
-// Y > 1e19.  The fast path sums a row's links lane-split + tree-reduced; whenever that sum is
-// within 1e-9 relative of the 1e19 threshold the row is REPLAYED in the reference's order
-// (ascending src, separate multiply and add) so the NaN decision is bit-identical.
+// Y > 1e19.  The fast path multiplies raw values and sums a row's links lane-split +
+// tree-reduced; a non-finite sum (some source was NaN/inf) makes the warp redo its links with
+// the fill, and whenever a sum is within 1e-9 relative of the 1e19 threshold the row is
+// REPLAYED in the reference's order (ascending src, separate multiply and add) so the NaN
+// decision is bit-identical.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
