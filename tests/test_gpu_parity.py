@@ -495,3 +495,38 @@ def test_renormalising_extension(smm_lib, oracle, cuda, xdt):
     # off again: bit-identical NaN pattern with the oracle's reference semantics
     y0 = Regridder(weights=w, remap_area_min=0.5).regrid(x).reshape(B, n_dst)
     assert_parity(y0, oracle.apply_weights_c(x, mat, None, w["dst_grid_frac"], 0.5, False), 1e-12, "reference mode")
+
+
+def test_levels_mixed_kernels_and_empty_level(smm_lib, oracle, cuda):
+    """A 3-D weight set whose levels need different kernel families (structured -> staged,
+    scattered -> gather) plus a level without any link; B = 1 as well."""
+    from smmregrid_b200 import CdoWeights, Regridder, synth
+    n_lon_s, n_lat_s, n_lon_d, n_lat_d = 576, 288, 72, 36
+    n_src, n_dst = n_lon_s * n_lat_s, n_lon_d * n_lat_d
+    con = synth.conservative_latlon(n_lon_s, n_lat_s, n_lon_d, n_lat_d)
+    sca = synth.scattered_weights(n_src, n_lon_d, n_lat_d, links_per_row=4, ordering="random", seed=2)
+    parts = [con, sca, None, con]                          # level 2 has no links at all
+    ll = np.array([0 if p is None else p["src_address"].size for p in parts], np.int64)
+    nl = int(ll.max())
+    sa = np.zeros((4, nl), np.int32); da = np.zeros((4, nl), np.int32); rm = np.zeros((4, nl, 1))
+    for l, p in enumerate(parts):
+        if p is not None:
+            sa[l, :ll[l]], da[l, :ll[l]], rm[l, :ll[l]] = p["src_address"], p["dst_address"], p["remap_matrix"]
+    v = dict(con.vars)
+    v.update(src_address=sa, dst_address=da, remap_matrix=rm, link_length=ll,
+             src_grid_imask=np.ones((4, n_src), np.int32), dst_grid_imask=np.ones((4, n_dst), np.int32),
+             dst_grid_frac=np.ones((4, n_dst)))
+    w = CdoWeights(v, mask_dim="lev", levels=[1.0, 2.0, 3.0, 4.0])
+    rg = Regridder(weights=w, remap_area_min=0.0)
+    kinds = [rg.weights_matrix.info(l)["kernel_name"] for l in range(4)]
+    assert kinds[0] == "staged" and kinds[1] == "gather" and kinds[3] == "staged", kinds
+    mats = oracle.compute_weights_matrix3d_np(sa, da, rm, ll, n_src, n_dst, builder=oracle.compute_weights_matrix_c)
+    imask = np.stack([oracle.mask_tensordot_c(np.ones(n_src, np.int32), m)[0] for m in mats])
+    masked = oracle.check_mask_np(imask)
+    assert masked.tolist() == [False, False, True, False] and np.array_equal(np.asarray(rg.masked), masked)
+    for T in (1, 7):
+        x = synth.synthetic_field((T, 4, n_src), np.float32, seed=T, nan_mode="random")
+        y_ref = oracle.regrid3d_np(x, 1, w.levels, w.levels, mats, imask, v["dst_grid_frac"], masked, 0.0)
+        y = rg.regrid(x).reshape(T, 4, n_dst)
+        assert_parity(y, y_ref, RTOL_F64, f"mixed T={T}")
+        assert np.isnan(y[:, 2]).all()                     # no links -> masked level -> NaN everywhere
