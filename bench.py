@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kernel", default="auto", choices=["auto", "staged", "gather"])
+    ap.add_argument("--nan", default="none", choices=["none", "land", "random"],
+                    help="missing values in the synthetic slab: none | land (static smooth land mask, ~35%%) | random (30%% of points)")
     return ap.parse_args()
 
 
@@ -277,6 +279,18 @@ def main():
     for b0 in range(0, B, 64):
         xb = x[b0:b0 + 64]
         xb.normal_(280.0, 20.0, generator=g)
+    if args.nan != "none" and not is3d:
+        if args.nan == "random":
+            m = torch.rand(n_src, generator=g, device=dev) < 0.3
+        else:       # smooth, contiguous "continents" (SURVEY 8d variant ii): same cells every step
+            ii = torch.arange(n_src, device=dev, dtype=torch.float32)
+            nlon = float(np.atleast_1d(w["src_grid_dims"])[0])
+            lon, lat = (ii % nlon) / nlon * 6.2832, torch.floor(ii / nlon) / (n_src / nlon) * 3.1416
+            m = (torch.sin(2 * lon + 0.5) * torch.sin(lat) + 0.6 * torch.cos(3 * lon - 1.0) * torch.sin(2 * lat)) > 0.25
+        x[:, m] = float("nan")
+        nan_frac = float(m.float().mean().item())
+    else:
+        nan_frac = 0.0
     y = torch.empty((B, n_dst), dtype=torch.float32 if args.ydtype == "f32" else torch.float64, device=dev)
     lib = _lib.load()
     stream = torch.cuda.current_stream(dev)
@@ -381,6 +395,7 @@ def main():
                    "n_src": n_src, "n_dst": n_dst, "nnz": info["nnz"], "x_dtype": args.xdtype,
                    "y_dtype": args.ydtype, "weights_dtype": "f64", "remap_area_min": area_min,
                    "kernel": info["kernel_name"], "lanes_per_row": info["lanes_per_row"],
+                   "nan": args.nan, "nan_fraction_of_source": round(nan_frac, 3),
                    "parallelism": f"batch-sharded x{world}, weights replicated, no collective",
                    "l2": "resident slab (%.1f GB) >> 126 MB L2, no flush" % (B * n_src * sx / 1e9)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -344,6 +344,8 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         const bool stream_only = (a.debug_flags & 1u) != 0;
 
         const int NB = a.rows_per_stage;
+        bool prefer_fill = false;      // warp-uniform: the previous batch row needed the 1e20 fill
+        uint32_t n_done = 0;
         int s = 0;
         uint32_t ph = 0;
         for (int64_t g = b0; g < b1; g += NB) {          // one stage = up to NB consecutive batch rows
@@ -358,16 +360,28 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
                     // fast path: raw values.  A non-finite partial means some source value was NaN/inf
                     // (regrid.py:545-547 fills those with 1e20): redo the warp's links with the fill --
                     // or, in the opt-in renormalising mode, without the missing sources.
-                    acc = lane_sum<TX, KPL, false>(sb, off, w);
-                    if (__any_sync(0xffffffffu, not_finite(acc))) {
-                        if (a.renorm_min_valid < 0.0) {
-                            acc = lane_sum<TX, KPL, true>(sb, off, w);
-                        } else {
-                            double s3[3];
-                            lane_sum_valid<TX, KPL, NCT>(job.wplan, job.iplan, static_cast<size_t>(tile) * KPL * NCT + tid, sb, s3);
-                            acc = renormalise(group_sum<LPR>(s3[0]), group_sum<LPR>(s3[1]), group_sum<LPR>(s3[2]),
-                                              a.renorm_min_valid);
-                            renormed = true;
+                    // Missing values are usually static (land/sea masks): a warp that needed the
+                    // fill for one batch row goes straight to the single-pass filled sum for the
+                    // following ones and re-probes the cheap path every 16 rows.
+                    const bool probe = !prefer_fill || (n_done & 15u) == 0;
+                    ++n_done;
+                    if (!probe) {
+                        acc = lane_sum<TX, KPL, true>(sb, off, w);
+                    } else {
+                        prefer_fill = false;
+                        acc = lane_sum<TX, KPL, false>(sb, off, w);
+                        if (__any_sync(0xffffffffu, not_finite(acc))) {
+                            if (a.renorm_min_valid < 0.0) {
+                                acc = lane_sum<TX, KPL, true>(sb, off, w);
+                                prefer_fill = true;
+                            } else {
+                                double s3[3];
+                                lane_sum_valid<TX, KPL, NCT>(job.wplan, job.iplan,
+                                                             static_cast<size_t>(tile) * KPL * NCT + tid, sb, s3);
+                                acc = renormalise(group_sum<LPR>(s3[0]), group_sum<LPR>(s3[1]), group_sum<LPR>(s3[2]),
+                                                  a.renorm_min_valid);
+                                renormed = true;
+                            }
                         }
                     }
                 }
