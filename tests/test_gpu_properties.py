@@ -1,6 +1,7 @@
 """Property tests on the GPU (hypothesis): random link sets, NaN/inf patterns, masks, dtypes and
 strides against the oracle -- both kernel families, every lane configuration."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -45,7 +46,8 @@ def cases(draw):
                 pad=draw(st.sampled_from([0, 4, 1])))
 
 
-@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@settings(max_examples=int(os.environ.get("SMM_HYP_EXAMPLES", "60")), deadline=None,
+          suppress_health_check=list(HealthCheck), derandomize=os.environ.get("SMM_HYP_RANDOM") is None)
 @given(c=cases())
 def test_random_operator_matches_oracle(smm_lib, oracle, cuda, c):
     import torch
