@@ -54,6 +54,9 @@ typedef struct smm_info {
     int32_t max_tile_segments;
     int32_t consumer_threads;    /* staged plan: link-holding threads per CTA (256 | 512)  */
     int32_t rows_reordered;      /* staged plan tiles rows re-ordered by mean source address */
+    int32_t packed_rows;         /* staged plan packs up to 4 short rows per thread (then  */
+                                 /* rows_per_tile is the most a tile can hold)             */
+    int32_t reserved;
     int64_t max_tile_elems;      /* largest staged source footprint of a tile (elements)  */
     int64_t sum_tile_elems;      /* sum of staged footprints: source elements one batch   */
                                  /* row pulls through TMA (>= touched columns)            */
@@ -180,6 +183,10 @@ int smm_host_plan_copy(const smm_host_plan *p, int32_t *rowptr, int32_t *col, do
                        int32_t *tiles, uint32_t *segs, double *wplan, uint16_t *iplan);
 /* rowmap [n_dst]: destination row held by every tile slot (only when info.rows_reordered). */
 int smm_host_plan_rowmap(const smm_host_plan *p, int32_t *rowmap);
+/* rowslot [n_tiles*4*consumer_threads] (only when info.packed_rows): destination row whose value
+ * starts in sub-row u (link slots 4u..4u+3) of thread t at [tile][u][t]; -1 none, -2 the sub-row
+ * continues the row of sub-row u-1. */
+int smm_host_plan_rowslot(const smm_host_plan *p, int32_t *rowslot);
 void smm_host_plan_free(smm_host_plan *p);
 
 /* Force a kernel family for subsequent applies (testing/benchmark aid): 0 = automatic,

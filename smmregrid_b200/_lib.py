@@ -25,7 +25,7 @@ class SmmInfo(ctypes.Structure):
         ("n_src", i64), ("n_dst", i64), ("nnz", i64),
         ("n_levels", i32), ("kernel", i32), ("lanes_per_row", i32), ("links_per_lane", i32),
         ("rows_per_tile", i32), ("n_tiles", i32), ("max_row_nnz", i32), ("max_tile_segments", i32),
-        ("consumer_threads", i32), ("rows_reordered", i32),
+        ("consumer_threads", i32), ("rows_reordered", i32), ("packed_rows", i32), ("reserved", i32),
         ("max_tile_elems", i64), ("sum_tile_elems", i64), ("touched_src", i64), ("device_bytes", i64),
     ]
 
@@ -51,6 +51,7 @@ SIGNATURES = {
     "smm_host_plan_info": (ctypes.c_int, [vp, P(SmmInfo), P(i64)]),
     "smm_host_plan_copy": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "smm_host_plan_rowmap": (ctypes.c_int, [vp, vp]),
+    "smm_host_plan_rowslot": (ctypes.c_int, [vp, vp]),
     "smm_host_plan_free": (None, [vp]),
     "smm_set_kernel": (ctypes.c_int, [vp, i32]),
     "smm_set_renormalize": (ctypes.c_int, [vp, f64]),

@@ -51,7 +51,8 @@ struct LevelDev {
     Seg *segs = nullptr;
     double *wplan = nullptr;
     uint16_t *iplan = nullptr;
-    int32_t *rowmap = nullptr;
+    int32_t *rowmap = nullptr;          // tile slot -> row (re-ordered plans) | packed plans: the rowslot table
+    bool packed = false, reordered = false;
     int32_t *imask = nullptr;
     double *frac = nullptr;
     bool has_imask = false, has_frac = false;
@@ -120,7 +121,10 @@ int upload_level(const HostCsr &csr, const HostPlan &plan, LevelDev &L)
         if ((rc = upload(&L.segs, plan.segs, L.device_bytes))) return rc;
         if ((rc = upload(&L.wplan, plan.wplan, L.device_bytes))) return rc;
         if ((rc = upload(&L.iplan, plan.iplan, L.device_bytes))) return rc;
-        if (!plan.rowmap.empty() && (rc = upload(&L.rowmap, plan.rowmap, L.device_bytes))) return rc;
+        L.packed = plan.packed;
+        L.reordered = plan.reordered;
+        if (plan.packed) { if ((rc = upload(&L.rowmap, plan.rowslot, L.device_bytes))) return rc; }
+        else if (!plan.rowmap.empty() && (rc = upload(&L.rowmap, plan.rowmap, L.device_bytes))) return rc;
     }
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&L.imask), static_cast<size_t>(L.n_dst) * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&L.frac), static_cast<size_t>(L.n_dst) * sizeof(double)));
@@ -156,15 +160,41 @@ struct DeviceGuard {
 
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// One layout for every level of a weight set, so that a grouped launch runs a single kernel:
+// lanes per row / links per lane from the longest row, or -- short rows everywhere -- the
+// packed-rows layout (a thread owns up to 4 rows) instead of mostly-padding lanes.
+struct PlanChoice {
+    bool cfg = false, packed = false;
+    int32_t lpr = 0, kpl = 0, nct = 256;
+};
+
+PlanChoice choose_plan(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count)
+{
+    PlanChoice pc;
+    int32_t max_row = 0;
+    int64_t pslots = 0;
+    for (const HostCsr &c : csrs) {
+        max_row = std::max(max_row, c.max_row_nnz);
+        const int64_t ps = packed_slots(c);
+        pslots = (ps < 0 || pslots < 0) ? -1 : pslots + ps;
+    }
+    pc.cfg = choose_lanes(max_row, pc.lpr, pc.kpl);
+    const int64_t nlev = static_cast<int64_t>(std::max<size_t>(csrs.size(), 1));
+    pc.packed = pc.cfg && prefer_packed(pslots, n_dst * nlev, pc.lpr, pc.kpl);
+    pc.nct = pc.packed ? default_consumer_threads(pslots / nlev / 16, 1, sm_count)
+                       : default_consumer_threads(n_dst, pc.cfg ? pc.lpr : 0, sm_count);
+    return pc;
+}
+
 // ------------------------------------------------------------------ launch dispatch
 
 template <typename TX, typename TY>
-int launch_staged_t(int lpr, int kpl, int nct, dim3 grid, size_t smem, cudaStream_t st, const JobBatch &jb,
-                    const ApplyArgs &a)
+int launch_staged_t(int lpr, int kpl, int nct, bool packed, dim3 grid, size_t smem, cudaStream_t st,
+                    const JobBatch &jb, const ApplyArgs &a)
 {
-#define SMM_CASE_N(L_, K_, N_)                                                                    \
-    if (lpr == L_ && kpl == K_ && nct == N_) {                                                    \
-        auto kfn = staged_kernel<TX, TY, L_, K_, N_>;                                             \
+#define SMM_CASE_P(L_, K_, N_, P_)                                                                \
+    if (lpr == L_ && kpl == K_ && nct == N_ && packed == P_) {                                    \
+        auto kfn = staged_kernel<TX, TY, L_, K_, N_, P_>;                                         \
         CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                       static_cast<int>(smem)));                                   \
         kfn<<<grid, N_ + 32 * producer_warps(N_), smem, st>>>(jb, a);                             \
@@ -172,12 +202,15 @@ int launch_staged_t(int lpr, int kpl, int nct, dim3 grid, size_t smem, cudaStrea
         g_launches.fetch_add(1, std::memory_order_relaxed);                                       \
         return SMM_OK;                                                                            \
     }
+#define SMM_CASE_N(L_, K_, N_) SMM_CASE_P(L_, K_, N_, false)
 #define SMM_CASE(L_, K_) SMM_CASE_N(L_, K_, 256) SMM_CASE_N(L_, K_, 512)
+    SMM_CASE_P(1, 16, 256, true) SMM_CASE_P(1, 16, 512, true)
     SMM_CASE(1, 4) SMM_CASE(2, 4) SMM_CASE(1, 8) SMM_CASE(1, 12) SMM_CASE(1, 16) SMM_CASE(2, 12)
     SMM_CASE(2, 14) SMM_CASE(2, 16) SMM_CASE(4, 12) SMM_CASE(4, 16) SMM_CASE(8, 12) SMM_CASE(8, 14)
     SMM_CASE(8, 16) SMM_CASE(16, 16) SMM_CASE(32, 16)
 #undef SMM_CASE
 #undef SMM_CASE_N
+#undef SMM_CASE_P
     return fail(SMM_ERR_INVALID, "no staged kernel for this lane configuration");
 }
 
@@ -240,6 +273,8 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
             return fail(SMM_ERR_INVALID, "remap_area_min > 0 but dst_grid_frac was never set for level " +
                                              std::to_string(s.level));
         bool ok = L.staged && h->force_kernel != SMM_KERNEL_GATHER;
+        // the renormalising extension is not implemented for packed-rows plans: gather kernel
+        ok = ok && !(L.packed && h->renorm_min_valid >= 0.0);
         // TMA bulk copies need 16-byte aligned rows and lengths
         ok = ok && (reinterpret_cast<uintptr_t>(s.x) % 16 == 0) && ((xbs * sx) % 16 == 0) &&
              ((L.n_src * sx) % 16 == 0);
@@ -270,19 +305,22 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         j.x = s.x; j.y = s.y; j.masked = s.masked; j.pad = 0;
     };
 
-    // ---- staged launches, kMaxJobs levels at a time
-    for (size_t g0 = 0; g0 < staged.size(); g0 += kMaxJobs) {
-        const size_t g1 = std::min(staged.size(), g0 + kMaxJobs);
+    // ---- staged launches, up to kMaxJobs levels at a time
+    const size_t staged_groups = (staged.size() + kMaxJobs - 1) / kMaxJobs;
+    const size_t staged_per = staged_groups ? (staged.size() + staged_groups - 1) / staged_groups : 1;   // balanced
+    for (size_t g0 = 0; g0 < staged.size(); g0 += staged_per) {
+        const size_t g1 = std::min(staged.size(), g0 + staged_per);
         JobBatch jb{};
         int64_t tiles_total = 0;
         size_t max_segs = 0, max_elems = 0;
         int lpr = 0, kpl = 0, nct = 256;
+        bool packed = false;
         for (size_t g = g0; g < g1; ++g) {
             const LevelDev &L = h->levels[staged[g].level];
             tiles_total += L.ntiles;
             max_segs = std::max<size_t>(max_segs, L.max_segs);
             max_elems = std::max<size_t>(max_elems, L.max_elems);
-            lpr = L.lpr; kpl = L.kpl; nct = L.nct;
+            lpr = L.lpr; kpl = L.kpl; nct = L.nct; packed = L.packed;
             a.n_src = L.n_src; a.n_dst = L.n_dst;
         }
         const size_t stage_off = kSmemHeader + round_up(max_segs * sizeof(Seg), 128);
@@ -324,7 +362,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         if (item > INT32_MAX) return fail(SMM_ERR_INVALID, "too many work items in one launch");
         if (item == 0) continue;
         const dim3 grid(static_cast<unsigned>(item));
-        const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, lpr, kpl, nct, grid, smem, st, jb, a);
+        const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, lpr, kpl, nct, packed, grid, smem, st, jb, a);
         if (rc) return rc;
     }
 
@@ -569,14 +607,11 @@ int smm_create_levels(int32_t n_levels, const int64_t *link_length, int64_t nl_m
         if (rc) { delete h; return fail(rc, (n_levels > 1 ? "level " + std::to_string(i) + ": " : "") + err); }
         max_row = std::max(max_row, csrs[i].max_row_nnz);
     }
-    // one lane configuration for every level so a grouped launch runs a single kernel
-    int32_t lpr = 0, kpl = 0;
-    const bool cfg = choose_lanes(max_row, lpr, kpl);
-    const int32_t nct = default_consumer_threads(n_dst, lpr, h->sm_count);
+    const PlanChoice pc = choose_plan(csrs, n_dst, h->sm_count);
     h->levels.resize(static_cast<size_t>(n_levels));
     for (int32_t i = 0; i < n_levels; ++i) {
         HostPlan plan;
-        if (cfg) build_plan(csrs[i], lpr, kpl, nct, plan);
+        if (pc.cfg) build_plan(csrs[i], pc.packed ? -1 : pc.lpr, pc.kpl, pc.nct, plan);
         else plan.why = "a destination row has more than 512 links";
         rc = upload_level(csrs[i], plan, h->levels[i]);
         if (rc) { smm_destroy(h); return rc; }
@@ -617,7 +652,8 @@ int smm_get_info(const smm_handle *h, int32_t level, smm_info *out)
     out->n_tiles = L.ntiles; out->max_row_nnz = L.max_row_nnz;
     out->max_tile_segments = L.max_segs; out->max_tile_elems = L.max_elems;
     out->consumer_threads = L.nct;
-    out->rows_reordered = L.rowmap ? 1 : 0;
+    out->rows_reordered = L.reordered ? 1 : 0;
+    out->packed_rows = L.packed ? 1 : 0;
     out->sum_tile_elems = L.sum_elems; out->touched_src = L.touched;
     out->device_bytes = L.device_bytes;
     return SMM_OK;
@@ -800,9 +836,12 @@ int smm_host_plan_build(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t
                        index_base, p->csr, err);
     if (rc) { delete p; return fail(rc, err); }
     {
-        int32_t lpr = 0, kpl = 0;
-        const bool cfg = choose_lanes(p->csr.max_row_nnz, lpr, kpl);
-        build_plan(p->csr, 0, 0, default_consumer_threads(n_dst, cfg ? lpr : 0, 148), p->plan);
+        std::vector<HostCsr> one(1);
+        one[0] = std::move(p->csr);
+        const PlanChoice pc = choose_plan(one, n_dst, 148);
+        p->csr = std::move(one[0]);
+        if (pc.cfg) build_plan(p->csr, pc.packed ? -1 : 0, 0, pc.nct, p->plan);
+        else p->plan.why = "a destination row has more than 512 links";
     }
     *out = p;
     return SMM_OK;
@@ -822,7 +861,8 @@ int smm_host_plan_info(const smm_host_plan *p, smm_info *out, int64_t *n_segs_ou
     out->max_row_nnz = p->csr.max_row_nnz;
     out->max_tile_segments = p->plan.max_tile_segments;
     out->consumer_threads = p->plan.nct;
-    out->rows_reordered = p->plan.rowmap.empty() ? 0 : 1;
+    out->rows_reordered = p->plan.reordered ? 1 : 0;
+    out->packed_rows = p->plan.packed ? 1 : 0;
     out->max_tile_elems = p->plan.max_tile_elems;
     out->sum_tile_elems = p->plan.sum_tile_elems;
     out->touched_src = p->csr.touched_src;
@@ -852,6 +892,13 @@ int smm_host_plan_rowmap(const smm_host_plan *p, int32_t *rowmap)
 {
     if (!p || !rowmap) return fail(SMM_ERR_INVALID, "null argument");
     if (!p->plan.rowmap.empty()) std::memcpy(rowmap, p->plan.rowmap.data(), p->plan.rowmap.size() * sizeof(int32_t));
+    return SMM_OK;
+}
+
+int smm_host_plan_rowslot(const smm_host_plan *p, int32_t *rowslot)
+{
+    if (!p || !rowslot) return fail(SMM_ERR_INVALID, "null argument");
+    if (!p->plan.rowslot.empty()) std::memcpy(rowslot, p->plan.rowslot.data(), p->plan.rowslot.size() * sizeof(int32_t));
     return SMM_OK;
 }
 

@@ -18,7 +18,7 @@ constexpr int kMaxStages = 12;
 constexpr int kSegAlign = 8;                        // segment bounds: multiples of 8 elements
 constexpr int kSegGap = 32;                         // merge segments closer than this
 constexpr int kSmemHeader = 256;                    // full[12] + empty[12] mbarriers
-constexpr int kMaxJobs = 24;                        // levels per grouped launch (by-value args)
+constexpr int kMaxJobs = 128;                       // levels per grouped launch (by-value args, 14 KB of the 32 KB parameter space)
 constexpr int kGatherThreads = 256;
 constexpr int kGatherBT = 4;                        // batch rows register-blocked by the gather kernel
 

@@ -125,9 +125,13 @@ __device__ __forceinline__ TY finish(double acc, bool dead, Replay replay)
 
 __device__ __forceinline__ const LevelJob &find_job(const JobBatch &jb, int item, int &j)
 {
-    j = 0;
+    int lo = 0, hi = jb.njobs - 1;                 // last job with item0 <= item
 #pragma unroll 1
-    while (j + 1 < jb.njobs && item >= jb.jobs[j + 1].item0) ++j;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (item >= jb.jobs[mid].item0) lo = mid; else hi = mid - 1;
+    }
+    j = lo;
     return jb.jobs[j];
 }
 
@@ -185,6 +189,23 @@ __device__ __forceinline__ double lane_sum(uint32_t sb, const uint32_t (&off)[KP
     return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
+// Packed rows: a thread's 16 links are four sub-rows of four; one partial sum per sub-row.
+template <typename TX, bool kFill>
+__device__ __forceinline__ void lane_sum4(uint32_t sb, const uint32_t (&off)[16], const double (&w)[16], double (&s4)[4])
+{
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        TX v0 = lds<TX>(sb + off[4 * u + 0]);
+        TX v1 = lds<TX>(sb + off[4 * u + 1]);
+        TX v2 = lds<TX>(sb + off[4 * u + 2]);
+        TX v3 = lds<TX>(sb + off[4 * u + 3]);
+        if (kFill) { v0 = fill_invalid(v0); v1 = fill_invalid(v1); v2 = fill_invalid(v2); v3 = fill_invalid(v3); }
+        const double e = fma(static_cast<double>(v1), w[4 * u + 1], static_cast<double>(v0) * w[4 * u + 0]);
+        const double o = fma(static_cast<double>(v3), w[4 * u + 3], static_cast<double>(v2) * w[4 * u + 2]);
+        s4[u] = e + o;
+    }
+}
+
 // Opt-in renormalising mode (extension, off by default): the sums a lane needs to
 // EXCLUDE non-finite sources instead of filling them: sum of w*x over finite x, sum of w over
 // finite x, sum of all w.
@@ -235,9 +256,17 @@ __device__ __forceinline__ bool not_finite(double v) { return !(fabs(v) <= 1.797
 #endif
 __host__ __device__ constexpr int producer_warps(int nct) { return nct == 512 ? SMM_PRODUCERS_512 : 4; }
 constexpr int kProducerRegs = 40;
-constexpr int kConsumerRegs = 96;
+#ifndef SMM_CONSUMER_REGS_512
+#define SMM_CONSUMER_REGS_512 104
+#endif
+// NCT = 512 launches 640 threads x 96 registers; the 56 x 128 the producers give back let the 512
+// consumers grow to 104 (4 consumer warps x 104 + 1 producer warp x 40 per sub-partition <= 512).
+__host__ __device__ constexpr int consumer_regs(int nct) { return nct == 512 ? SMM_CONSUMER_REGS_512 : 96; }
 
-template <typename TX, typename TY, int LPR, int KPL, int NCT>
+// PACKED (LPR = 1, KPL = 16): a thread owns up to four short destination rows, one per 4-link
+// sub-row (a longer row continues into the next sub-rows); job.rowmap then holds
+// [ntiles][4][NCT] = destination row of a sub-row, -1 empty, -2 continuation of the previous one.
+template <typename TX, typename TY, int LPR, int KPL, int NCT, bool PACKED = false>
 __global__ void __launch_bounds__(NCT + 32 * producer_warps(NCT), NCT == 256 ? 2 : 1)
 staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ ApplyArgs a)
 {
@@ -316,12 +345,12 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         }
     } else {
         // ---------------- consumer warps: links live in registers for the whole batch loop
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(consumer_regs(NCT)));
         const int r_in = tid / LPR;
         const int l_in = tid % LPR;
         const bool valid = r_in < td.nrows;
         // td.row0 is the tile's first slot; plans built on a re-ordered row sequence map slots to rows
-        const int row = (job.rowmap && valid) ? job.rowmap[td.row0 + r_in] : td.row0 + r_in;
+        const int row = (!PACKED && job.rowmap && valid) ? job.rowmap[td.row0 + r_in] : td.row0 + r_in;
 
         double w[KPL];
         uint32_t off[KPL];
@@ -333,6 +362,72 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
                 off[k] = static_cast<uint32_t>(__ldg(job.iplan + base + static_cast<size_t>(k) * NCT)) *
                          static_cast<uint32_t>(sizeof(TX));
             }
+        }
+        if constexpr (PACKED) {
+            static_assert(LPR == 1 && KPL == 16, "packed rows: 4 sub-rows of 4 links per thread");
+            int rs[4];                  // destination row per sub-row (-1 none)
+            uint32_t flags = 0;         // bit u: sub-row u continues u-1; bit 4+u: row of sub-row u is dead
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                rs[u] = __ldg(job.rowmap + (static_cast<size_t>(tile) * 4 + u) * NCT + tid);
+                if (rs[u] == -2) flags |= 1u << u;
+                if (rs[u] >= 0) {
+                    bool dead = false;
+                    if (job.masked && job.imask[rs[u]] == 0) dead = true;
+                    if (a.remap_area_min > 0.0 && job.frac[rs[u]] < a.remap_area_min) dead = true;
+                    if (dead) flags |= 16u << u;
+                }
+            }
+            TY *yb = static_cast<TY *>(job.y) + b0 * a.y_bstride;
+            const TX *xp = static_cast<const TX *>(job.x) + b0 * a.x_bstride;
+            const bool stream_only = (a.debug_flags & 1u) != 0;
+            const int NB = a.rows_per_stage;
+            bool prefer_fill = false;
+            uint32_t n_done = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t g = b0; g < b1; g += NB) {
+                const int nb = (g + NB <= b1) ? NB : static_cast<int>(b1 - g);
+                mbar_wait(full_addr + 8 * s, ph);
+                uint32_t sb = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
+#pragma unroll 1
+                for (int n = 0; n < nb; ++n, sb += a.row_bytes, yb += a.y_bstride, xp += a.x_bstride) {
+                    double s4[4] = {0.0, 0.0, 0.0, 0.0};
+                    if (!stream_only) {
+                        // same fast / filled / adaptive scheme as the lane-per-row consumers below
+                        const bool probe = !prefer_fill || (n_done & 15u) == 0;
+                        ++n_done;
+                        if (!probe) {
+                            lane_sum4<TX, true>(sb, off, w, s4);
+                        } else {
+                            prefer_fill = false;
+                            lane_sum4<TX, false>(sb, off, w, s4);
+                            if (__any_sync(0xffffffffu, not_finite((s4[0] + s4[1]) + (s4[2] + s4[3])))) {
+                                lane_sum4<TX, true>(sb, off, w, s4);
+                                prefer_fill = true;
+                            }
+                        }
+                    }
+                    if (n == nb - 1) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(empty_addr + 8 * s);
+                    }
+                    // a row's value = its first sub-row + the continuation sub-rows behind it
+                    double acc[4];
+                    acc[3] = s4[3];
+                    acc[2] = s4[2] + ((flags & 8u) ? acc[3] : 0.0);
+                    acc[1] = s4[1] + ((flags & 4u) ? acc[2] : 0.0);
+                    acc[0] = s4[0] + ((flags & 2u) ? acc[1] : 0.0);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (rs[u] >= 0)
+                            yb[rs[u]] = finish<TY>(acc[u], (flags & (16u << u)) != 0,
+                                                   [&]() { return replay_row<TX>(job.rowptr, job.col, job.val, rs[u], xp); });
+                    }
+                }
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+            return;
         }
         bool dead = false;
         if (valid) {

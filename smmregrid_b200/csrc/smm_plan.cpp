@@ -129,13 +129,22 @@ int32_t default_consumer_threads(int64_t n_dst, int32_t lpr, int32_t sm_count)
     return tiles512 >= sm_count ? 512 : 256;
 }
 
+// Packed rows (short-row operators: nn, bilinear, 1:1 conservative, ocean levels): a thread's 16
+// link slots are four sub-rows of four; a row takes 1-4 consecutive sub-rows of ONE thread, so a
+// thread owns up to four destination rows and a tile up to 4*NCT.  Fewer, fuller consumer
+// iterations where the lane-per-row layout would mostly multiply padding.
+constexpr int kSubRows = 4, kSubLinks = 4;
+
 static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct,
-                               const std::vector<int32_t> *order, HostPlan &plan)
+                               const std::vector<int32_t> *order, bool packed, HostPlan &plan)
 {
     plan = HostPlan{};
     if (nct != 256 && nct != 512) nct = 256;
     int32_t lpr = force_lpr, kpl = force_kpl;
-    if (lpr <= 0 || kpl <= 0) {
+    if (packed) {
+        if (csr.max_row_nnz > kSubRows * kSubLinks) { plan.why = "row too long for the packed layout"; return; }
+        lpr = 1; kpl = kSubRows * kSubLinks;
+    } else if (lpr <= 0 || kpl <= 0) {
         if (!choose_lanes(csr.max_row_nnz, lpr, kpl)) {
             plan.why = "a destination row has more than 512 links";
             return;
@@ -145,10 +154,49 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
         return;
     }
     const int64_t n_dst = csr.n_dst, n_src = csr.n_src;
-    const int32_t R = nct / lpr;
-    const int64_t ntiles = (n_dst + R - 1) / R;
+    const int32_t R = packed ? nct * kSubRows : nct / lpr;          // most rows a tile can hold
+    auto row_at = [&](int64_t pos) -> int64_t { return order ? (*order)[pos] : pos; };
+    // tile boundaries (positions in the row order); packed: also every row's (thread, sub-row)
+    std::vector<int64_t> tile_start;
+    std::vector<int32_t> row_thread;
+    std::vector<int8_t> row_sub;
+    if (!packed) {
+        for (int64_t r = 0; r < n_dst; r += R) tile_start.push_back(r);
+    } else {
+        // Rows are dealt round-robin over the 32 lanes of a warp (lane l's j-th row is about
+        // row base + 32*j + l): the lanes of a warp read neighbouring source elements and write
+        // neighbouring destination cells in every slot, like the lane-per-row layout does.
+        row_thread.resize(static_cast<size_t>(n_dst));
+        row_sub.resize(static_cast<size_t>(n_dst));
+        const int32_t nwarps = nct / 32;
+        int32_t wi = 0, next = 0;
+        int8_t used[32] = {0};
+        tile_start.push_back(0);
+        for (int64_t pos = 0; pos < n_dst; ++pos) {
+            const int64_t r = row_at(pos);
+            const int32_t nnz = csr.rowptr[r + 1] - csr.rowptr[r];
+            const int32_t c = std::max(1, (nnz + kSubLinks - 1) / kSubLinks);
+            int32_t lane = -1;
+            for (int32_t tries = 0; tries < 32 && lane < 0; ++tries) {
+                const int32_t l = (next + tries) & 31;
+                if (used[l] + c <= kSubRows) lane = l;
+            }
+            if (lane < 0) {                                // warp full: next warp, maybe next tile
+                if (++wi == nwarps) { wi = 0; tile_start.push_back(pos); }
+                std::fill(used, used + 32, static_cast<int8_t>(0));
+                lane = 0;
+            }
+            row_thread[pos] = wi * 32 + lane;
+            row_sub[pos] = used[lane];
+            used[lane] = static_cast<int8_t>(used[lane] + c);
+            next = (lane + 1) & 31;
+        }
+    }
+    const int64_t ntiles = static_cast<int64_t>(tile_start.size());
+    tile_start.push_back(n_dst);
     if (ntiles > INT32_MAX / 2) { plan.why = "too many tiles"; return; }
-    plan.lpr = lpr; plan.kpl = kpl; plan.rows_per_tile = R; plan.nct = nct;
+    plan.lpr = lpr; plan.kpl = kpl; plan.rows_per_tile = R; plan.nct = nct; plan.packed = packed;
+    if (packed) plan.rowslot.assign(static_cast<size_t>(ntiles) * kSubRows * nct, -1);
     plan.tiles.resize(static_cast<size_t>(ntiles));
     plan.wplan.assign(static_cast<size_t>(ntiles) * kpl * nct, 0.0);
     plan.iplan.assign(static_cast<size_t>(ntiles) * kpl * nct, 0);
@@ -165,8 +213,7 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
     auto work = [&](Part &out) {
     std::vector<int32_t> cols;
     for (int64_t t = out.t0; t < out.t1; ++t) {
-        const int64_t r0 = t * R, r1 = std::min(n_dst, r0 + R);      // positions in the row order
-        auto row_at = [&](int64_t pos) -> int64_t { return order ? (*order)[pos] : pos; };
+        const int64_t r0 = tile_start[t], r1 = tile_start[t + 1];       // positions in the row order
         if (!order) {
             cols.assign(csr.col.begin() + csr.rowptr[r0], csr.col.begin() + csr.rowptr[r1]);
         } else {
@@ -223,6 +270,47 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
         // a NaN the row does not own).
         const Seg *sb = out.segs.data() + td.seg0;
         const size_t tbase = static_cast<size_t>(t) * kpl * nct;
+        auto local_index = [&](uint32_t c) -> uint32_t {      // footprint-local element of source column c
+            int lo = 0, hi = td.nseg - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (sb[mid].src <= c) lo = mid; else hi = mid - 1;
+            }
+            return sb[lo].dst + (c - sb[lo].src);
+        };
+        if (packed) {
+            // rows in order, each into its 1-4 sub-rows; padding slots (weight 0) re-read a link of
+            // the row that owns the sub-row, empty sub-rows a link of the thread's first row
+            const size_t sbase = static_cast<size_t>(t) * kSubRows * nct;
+            std::vector<int32_t> thread_first(static_cast<size_t>(nct), -1);
+            for (int64_t pos = r0; pos < r1; ++pos) {
+                const int64_t r = row_at(pos);
+                const int32_t thread = row_thread[pos], u0 = row_sub[pos];
+                const int32_t a = csr.rowptr[r], b = csr.rowptr[r + 1];
+                const int32_t c = std::max(1, (b - a + kSubLinks - 1) / kSubLinks);
+                plan.rowslot[sbase + static_cast<size_t>(u0) * nct + thread] = static_cast<int32_t>(r);
+                for (int32_t u = 1; u < c; ++u) plan.rowslot[sbase + static_cast<size_t>(u0 + u) * nct + thread] = -2;
+                uint16_t first_li = 0;
+                for (int32_t j = a; j < b; ++j) {
+                    const uint32_t li = local_index(static_cast<uint32_t>(csr.col[j]));
+                    const int32_t k = u0 * kSubLinks + (j - a);
+                    plan.wplan[tbase + static_cast<size_t>(k) * nct + thread] = csr.val[j];
+                    plan.iplan[tbase + static_cast<size_t>(k) * nct + thread] = static_cast<uint16_t>(li);
+                    if (j == a) first_li = static_cast<uint16_t>(li);
+                }
+                if (b > a && thread_first[thread] < 0) thread_first[thread] = first_li;
+                for (int32_t k = u0 * kSubLinks + (b - a); k < (u0 + c) * kSubLinks; ++k)
+                    plan.iplan[tbase + static_cast<size_t>(k) * nct + thread] = first_li;
+            }
+            for (int32_t thread = 0; thread < nct; ++thread) {
+                if (thread_first[thread] < 0) continue;
+                for (int32_t u = 0; u < kSubRows; ++u)
+                    if (plan.rowslot[sbase + static_cast<size_t>(u) * nct + thread] == -1)
+                        for (int32_t k = u * kSubLinks; k < (u + 1) * kSubLinks; ++k)
+                            plan.iplan[tbase + static_cast<size_t>(k) * nct + thread] = static_cast<uint16_t>(thread_first[thread]);
+            }
+            continue;
+        }
         const int rows_per_warp = 32 / lpr;
         const int nwarps = nct / 32;
         struct Link { uint16_t li; double w; };
@@ -381,7 +469,8 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
         plan.why = "staged footprint over-reads the touched sectors";
         return;
     }
-    if (order) plan.rowmap = *order;
+    if (order && !packed) plan.rowmap = *order;      // packed plans carry row ids in rowslot
+    plan.reordered = order != nullptr;
     plan.ok = true;
 }
 
@@ -391,9 +480,33 @@ static double plan_cost(const HostPlan &p)
     return static_cast<double>(p.sum_tile_elems) + 64.0 * static_cast<double>(p.segs.size());
 }
 
+// Link slots the packed layout spends on this operator (4*ceil(nnz/4) per row, at least one
+// sub-row), or -1 when a row does not fit a thread.  Packing pays when this is well below the
+// rows * links_per_lane slots of the lane-per-row layout (mostly padding for short rows).
+int64_t packed_slots(const HostCsr &csr)
+{
+    if (csr.max_row_nnz > kSubRows * kSubLinks) return -1;
+    int64_t slots = 0;
+    for (int64_t r = 0; r < csr.n_dst; ++r) {
+        const int32_t nnz = csr.rowptr[r + 1] - csr.rowptr[r];
+        slots += kSubLinks * std::max(1, (nnz + kSubLinks - 1) / kSubLinks);
+    }
+    return slots;
+}
+
+bool prefer_packed(int64_t slots_packed, int64_t rows, int32_t lpr, int32_t kpl)
+{
+    if (slots_packed < 0) return false;
+    if (const char *e = std::getenv("SMM_PACKED")) return e[0] == '1';
+    if (lpr != 1 || rows == 0) return false;
+    return static_cast<double>(slots_packed) <= 0.7 * static_cast<double>(rows) * kpl;
+}
+
 void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, HostPlan &plan)
 {
-    build_plan_ordered(csr, force_lpr, force_kpl, nct, nullptr, plan);
+    const bool packed = force_lpr == -1;       // -1: packed layout requested (see smm_create_levels)
+    if (packed) { force_lpr = 0; force_kpl = 0; }
+    build_plan_ordered(csr, force_lpr, force_kpl, nct, nullptr, packed, plan);
     if (plan.lpr == 0 || csr.col.empty()) return;
     // natural order good enough: footprints within 30 % of the columns actually touched
     if (plan.ok && plan_cost(plan) <= 1.3 * static_cast<double>(plan.sum_tile_cols)) return;
@@ -410,7 +523,7 @@ void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return key[x] < key[y]; });
     HostPlan alt;
-    build_plan_ordered(csr, force_lpr, force_kpl, nct, &order, alt);
+    build_plan_ordered(csr, force_lpr, force_kpl, nct, &order, packed, alt);
     if (alt.ok && (!plan.ok || plan_cost(alt) < 0.8 * plan_cost(plan))) plan = std::move(alt);
 }
 

@@ -33,6 +33,9 @@ struct HostPlan {
     std::vector<TileDesc> tiles;
     std::vector<Seg> segs;
     std::vector<int32_t> rowmap;   // empty: tile t holds rows [t*R, ...); else destination row of every tile slot
+    bool reordered = false;        // rows were tiled in mean-source-address order
+    bool packed = false;           // packed-rows plan: one thread owns up to 4 short rows (4 link slots each)
+    std::vector<int32_t> rowslot;  // packed: [ntiles][4][nct] destination row of a sub-row, -1 empty, -2 continuation
     std::vector<double> wplan;     // [ntiles][kpl][nct]
     std::vector<uint16_t> iplan;   // [ntiles][kpl][nct]
     int32_t max_tile_segments = 0;
@@ -51,7 +54,13 @@ bool choose_lanes(int32_t max_row_nnz, int32_t &lpr, int32_t &kpl);
 // footprints) a second plan is tried with the rows re-ordered by the mean source address of
 // their links, which turns locality-preserving unstructured orderings (HEALPix nested, Morton /
 // partition-ordered meshes) into compact per-tile footprints.
+// force_lpr == -1 requests the packed-rows layout (see prefer_packed).
 void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, HostPlan &plan);
+
+// Packed-rows layout (one thread owns up to 4 short rows): link slots it would spend on `csr`
+// (-1: a row does not fit) and whether that beats `rows` lane-per-row rows of `kpl` slots.
+int64_t packed_slots(const HostCsr &csr);
+bool prefer_packed(int64_t slots_packed, int64_t rows, int32_t lpr, int32_t kpl);
 
 // Consumer threads per CTA for a weight set: 512 (one CTA per SM, tiles twice as long, longer TMA
 // segments: +4 % on C4, +5 % on C2) when that still leaves at least one tile per SM, else 256.

@@ -530,3 +530,88 @@ def test_levels_mixed_kernels_and_empty_level(smm_lib, oracle, cuda):
         y = rg.regrid(x).reshape(T, 4, n_dst)
         assert_parity(y, y_ref, RTOL_F64, f"mixed T={T}")
         assert np.isnan(y[:, 2]).all()                     # no links -> masked level -> NaN everywhere
+
+
+def _short_row_links(rng, n_src, n_dst, choices, spread=6):
+    counts = rng.choice(choices, size=n_dst)
+    dst = np.repeat(np.arange(n_dst), counts)
+    src = np.clip((dst * n_src) // n_dst + rng.integers(-spread, spread + 1, size=dst.size), 0, n_src - 1)
+    w = rng.random(dst.size) + 0.05
+    o = np.lexsort((src, dst))
+    return src[o] + 1, dst[o] + 1, w[o].reshape(-1, 1)
+
+
+@pytest.mark.parametrize("xdt", [np.float32, np.float64])
+@pytest.mark.parametrize("ydt", [np.float64, np.float32])
+@pytest.mark.parametrize("n_dst", [3001, 420000])
+def test_packed_rows_parity(smm_lib, oracle, cuda, xdt, ydt, n_dst):
+    """Short-row operators run the packed-rows layout (a thread owns up to 4 rows; 256- and
+    512-thread tiles): missing values (static and per step), masks, frac, both output types."""
+    rng = np.random.default_rng(n_dst)
+    n_src = n_dst * 3 // 2 + 8
+    B = 37 if n_dst < 10000 else 5
+    src, dst, w = _short_row_links(rng, n_src, n_dst, [0, 1, 2, 3, 4, 4, 4, 5, 6, 9, 16])
+    x = (280 + 20 * rng.standard_normal((B, n_src))).astype(xdt)
+    x[:, rng.random(n_src) < 0.05] = np.nan                # static mask
+    x[rng.random(x.shape) < 0.002] = np.nan                # per-step holes
+    x[1, 77] = np.inf
+    x[2, 99] = -np.inf
+    imask = (rng.random(n_dst) > 0.1).astype(np.int32)
+    frac = rng.random(n_dst)
+    mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, imask, frac, 0.5, True, nthreads=4)
+    h = _create(smm_lib, src, dst, w, n_src, n_dst)
+    try:
+        inf = _info(smm_lib, h)
+        assert inf["kernel_name"] == "staged" and inf["packed_rows"] == 1, inf
+        assert inf["consumer_threads"] == (256 if n_dst < 10000 else 512), inf
+        y = _apply(smm_lib, h, x, n_dst, ydt, True, 0.5, imask, frac)
+        if ydt == np.float32:
+            y_ref = y_ref.astype(np.float32)
+        assert_parity(y, y_ref, RTOL_F64 if ydt == np.float64 else RTOL_F32, "packed")
+    finally:
+        smm_lib.smm_destroy(h)
+
+
+def test_packed_rows_threshold_replay_and_renorm(smm_lib, oracle, cuda):
+    """Packed plans: sums within rounding of 1e19 are replayed in the reference order (rows that
+    span two sub-rows included); the renormalising extension falls back to the gather kernel."""
+    rng = np.random.default_rng(21)
+    n_src, n_dst, B, k = 4096, 1500, 16, 8
+    dst = np.repeat(np.arange(n_dst), k)
+    src = (np.repeat(np.arange(n_dst) * 2, k) + np.tile(np.arange(k), n_dst)) % n_src
+    w = np.full(dst.size, 1.0 / k) + rng.uniform(-1e-17, 1e-17, size=dst.size)
+    # two of three rows are short, so the operator packs; every third keeps its 8 links
+    keep = (dst % 3 == 0) | (np.tile(np.arange(k), n_dst) < 2)
+    src, dst, w = src[keep], dst[keep], w[keep]
+    w[dst % 3 != 0] = 0.05 + rng.uniform(-1e-17, 1e-17, size=(dst % 3 != 0).sum())
+    o = np.lexsort((src, dst))
+    src, dst, w = src[o] + 1, dst[o] + 1, w[o].reshape(-1, 1)
+    x = rng.uniform(0, 2000, size=(B, n_src))              # float64: the fill is exactly 1e20
+    for d in range(n_dst):                                 # missing links put sums at 0.1 * 1e20 +- rounding
+        nbad = 2 if d % 3 else 1
+        cols = (d * 2 + rng.choice(2 if d % 3 else k, size=nbad, replace=False)) % n_src
+        x[d % B, cols] = np.nan
+    mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False)
+    near = np.abs(y_ref - 1e19) < 1e10
+    assert near.sum() > 100 and 0 < np.isnan(y_ref).sum() < y_ref.size
+    h = _create(smm_lib, src, dst, w, n_src, n_dst)
+    try:
+        assert _info(smm_lib, h)["packed_rows"] == 1
+        y = _apply(smm_lib, h, x, n_dst, np.float64, False, 0.0)
+        assert np.array_equal(np.isnan(y), np.isnan(y_ref))
+        assert np.array_equal(y[near], y_ref[near]), "replayed rows must be bit-identical"
+        assert_parity(y, y_ref, RTOL_F64, "packed threshold")
+        # renormalising extension on a packed plan
+        from smmregrid_b200 import _lib
+        _lib.check(smm_lib.smm_set_renormalize(h, 0.3))
+        n0 = smm_lib.smm_launch_count()
+        yr = _apply(smm_lib, h, x, n_dst, np.float64, False, 0.0)
+        assert smm_lib.smm_launch_count() == n0 + 1
+        ref = oracle.apply_weights_renorm_np(x, mat, np.ones(n_dst, np.int32), None, 0.0, False, 0.3)
+        assert_parity(yr, ref, 1e-12, "packed renorm -> gather")
+        _lib.check(smm_lib.smm_set_renormalize(h, -1.0))
+        assert_parity(_apply(smm_lib, h, x, n_dst, np.float64, False, 0.0), y_ref, RTOL_F64, "back to reference mode")
+    finally:
+        smm_lib.smm_destroy(h)

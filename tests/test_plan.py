@@ -43,6 +43,10 @@ class HostPlan:
         if inf.rows_reordered:
             self.rowmap = np.empty(n_dst, np.int32)
             _lib.check(lib.smm_host_plan_rowmap(h, self.rowmap.ctypes.data))
+        self.rowslot = None
+        if inf.packed_rows:
+            self.rowslot = np.empty((nt, 4, nct), np.int32)
+            _lib.check(lib.smm_host_plan_rowslot(h, self.rowslot.ctypes.data))
         lib.smm_host_plan_free(h)
 
     def emulate(self, x):
@@ -54,6 +58,16 @@ class HostPlan:
             stage = np.zeros((B, max(elems, 1)))
             for s, d, ln, _p in self.segs[seg0:seg0 + nseg]:
                 stage[:, d:d + ln] = x[:, s:s + ln]
+            if self.rowslot is not None:
+                # packed rows: thread = 4 sub-rows of 4 links; a row = its first sub-row + continuations
+                sub = (stage[:, self.iplan[t]] * self.wplan[t][None]).reshape(B, 4, 4, self.nct).sum(axis=2)
+                rs = self.rowslot[t]
+                for u in (2, 1, 0):
+                    sub[:, u] += np.where(rs[u + 1] == -2, sub[:, u + 1], 0.0)
+                own = rs >= 0
+                assert own.sum() == nrows
+                y[:, rs[own]] = sub[:, own]
+                continue
             lane = (stage[:, self.iplan[t]] * self.wplan[t][None]).sum(axis=1)      # [B, nct]
             rows = lane.reshape(B, self.nct // lpr, lpr).sum(axis=2)
             if self.rowmap is None:
@@ -195,3 +209,41 @@ def test_ang2pix_nest_known_values():
     la, lo = np.meshgrid(np.linspace(-89.9, 89.9, 400), np.linspace(0.1, 359.9, 800), indexing="ij")
     pix = ang2pix_nest(2, la, lo)
     assert pix.min() == 0 and pix.max() == 47 and np.unique(pix).size == 48
+
+
+@pytest.mark.parametrize("reorder", [False, True])
+def test_packed_rows_plan(smm_lib, oracle, reorder):
+    """Short-row operators (max <= 16 links, mostly <= 4): a thread owns up to four rows."""
+    rng = np.random.default_rng(11)
+    n_src, n_dst, B = 6000, 5003, 3
+    counts = rng.choice([0, 1, 2, 3, 4, 4, 4, 6, 9, 13, 16], size=n_dst)
+    dst = np.repeat(np.arange(n_dst), counts)
+    centre = (dst * n_src) // n_dst
+    if reorder:                                           # rows permuted: natural tiles would be scattered
+        perm = rng.permutation(n_dst)
+        centre = (perm[dst] * n_src) // n_dst
+    src = np.clip(centre + rng.integers(-12, 12, size=dst.size), 0, n_src - 1)
+    w = rng.random((dst.size, 1))
+    p = HostPlan(smm_lib, src + 1, dst + 1, w, n_src, n_dst)
+    assert p.info["kernel_name"] == "staged" and p.info["packed_rows"] == 1, p.info
+    assert (p.info["lanes_per_row"], p.info["links_per_lane"]) == (1, 16)
+    assert bool(p.info["rows_reordered"]) == reorder
+    _check_plan_invariants(p, n_src)
+    rs = p.rowslot
+    assert np.array_equal(np.sort(rs[rs >= 0]), np.arange(n_dst))        # every row exactly once
+    assert not (rs[:, 0] == -2).any()                                     # a continuation follows a row
+    need = np.maximum(1, -(-np.diff(p.rowptr) // 4))                      # sub-rows per row
+    assert (rs == -2).sum() == (need - 1).sum()
+    # padding slots carry weight 0; links sit in their row's sub-rows in ascending-src order
+    assert np.count_nonzero(p.wplan) == np.count_nonzero(p.val)
+    mat = oracle.compute_weights_matrix_c(src + 1, dst + 1, w, n_src, n_dst)
+    x = rng.standard_normal((B, n_src)) + 3
+    assert_parity(p.emulate(x), oracle.apply_weights_c(x, mat, None, None, 0.0, False), 1e-12)
+
+
+def test_packed_rows_not_used_for_uniform_rows(smm_lib):
+    from smmregrid_b200 import synth
+    w = synth.config_weights("C1", 1)                    # bilinear: 4 links in every row, nothing to pack
+    p = HostPlan(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"],
+                 w.sizes["src_grid_size"], w.sizes["dst_grid_size"])
+    assert p.info["packed_rows"] == 0 and (p.info["lanes_per_row"], p.info["links_per_lane"]) == (1, 4)
