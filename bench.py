@@ -72,6 +72,10 @@ def workload(name):
         _, a, b = name.split(":")
         (ls, ts), (ld, td) = [tuple(int(v) for v in g.split("x")) for g in (a, b)]
         return synth.conservative_latlon(ls, ts, ld, td), 1024, f"remapcon {ls}x{ts} -> {ld}x{td}"
+    if name.startswith("bil:"):          # bil:<nlon_s>x<nlat_s>:<nlon_d>x<nlat_d>  (experiments)
+        _, a, b = name.split(":")
+        (ls, ts), (ld, td) = [tuple(int(v) for v in g.split("x")) for g in (a, b)]
+        return synth.bilinear_latlon(ls, ts, ld, td), 256, f"remapbil {ls}x{ts} -> {ld}x{td}"
     raise SystemExit(f"unknown workload {name}")
 
 

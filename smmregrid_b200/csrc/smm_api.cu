@@ -161,8 +161,8 @@ struct DeviceGuard {
 inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // One layout for every level of a weight set, so that a grouped launch runs a single kernel:
-// lanes per row / links per lane from the longest row, or -- short rows everywhere -- the
-// packed-rows layout (a thread owns up to 4 rows) instead of mostly-padding lanes.
+// lanes per row / links per lane from the longest row, or -- no row above 16 links anywhere --
+// the packed-rows layout (a thread owns up to 4 rows).
 struct PlanChoice {
     bool cfg = false, packed = false;
     int32_t lpr = 0, kpl = 0, nct = 256;
@@ -180,10 +180,32 @@ PlanChoice choose_plan(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_c
     }
     pc.cfg = choose_lanes(max_row, pc.lpr, pc.kpl);
     const int64_t nlev = static_cast<int64_t>(std::max<size_t>(csrs.size(), 1));
-    pc.packed = pc.cfg && prefer_packed(pslots, n_dst * nlev, pc.lpr, pc.kpl);
+    pc.packed = pc.cfg && prefer_packed(pslots);
     pc.nct = pc.packed ? default_consumer_threads(pslots / nlev / 16, 1, sm_count)
                        : default_consumer_threads(n_dst, pc.cfg ? pc.lpr : 0, sm_count);
     return pc;
+}
+
+// Tile plans of all levels.  A packed tile holds 4x the rows, so its footprint may not fit where
+// the lane-per-row tile's does: if any level's packed plan is unusable, all levels fall back to
+// the lane-per-row layout (one kernel per grouped launch).
+void plan_levels(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, std::vector<HostPlan> &plans)
+{
+    PlanChoice pc = choose_plan(csrs, n_dst, sm_count);
+    plans.assign(csrs.size(), HostPlan{});
+    for (int pass = 0; pass < 2; ++pass) {
+        bool retry = false;
+        for (size_t i = 0; i < csrs.size(); ++i) {
+            plans[i] = HostPlan{};
+            if (!pc.cfg) { plans[i].why = "a destination row has more than 512 links"; continue; }
+            build_plan(csrs[i], pc.packed ? -1 : pc.lpr, pc.kpl, pc.nct, plans[i]);
+            // only a footprint that is too large can be cured by smaller tiles
+            if (pc.packed && !plans[i].ok && plans[i].why.rfind("tile footprint", 0) == 0) { retry = true; break; }
+        }
+        if (!retry) return;
+        pc.packed = false;
+        pc.nct = default_consumer_threads(n_dst, pc.lpr, sm_count);
+    }
 }
 
 // ------------------------------------------------------------------ launch dispatch
@@ -597,7 +619,6 @@ int smm_create_levels(int32_t n_levels, const int64_t *link_length, int64_t nl_m
 
     std::vector<HostCsr> csrs(static_cast<size_t>(n_levels));
     std::string err;
-    int32_t max_row = 0;
     for (int32_t i = 0; i < n_levels; ++i) {
         const int64_t o = static_cast<int64_t>(i) * nl_max;
         rc = build_csr(n_src, n_dst, link_length[i], src_address ? src_address + o : nullptr,
@@ -605,17 +626,15 @@ int smm_create_levels(int32_t n_levels, const int64_t *link_length, int64_t nl_m
                        remap_matrix ? remap_matrix + o * num_wgts : nullptr, num_wgts, index_base,
                        csrs[i], err);
         if (rc) { delete h; return fail(rc, (n_levels > 1 ? "level " + std::to_string(i) + ": " : "") + err); }
-        max_row = std::max(max_row, csrs[i].max_row_nnz);
     }
-    const PlanChoice pc = choose_plan(csrs, n_dst, h->sm_count);
+    std::vector<HostPlan> plans;
+    plan_levels(csrs, n_dst, h->sm_count, plans);
     h->levels.resize(static_cast<size_t>(n_levels));
     for (int32_t i = 0; i < n_levels; ++i) {
-        HostPlan plan;
-        if (pc.cfg) build_plan(csrs[i], pc.packed ? -1 : pc.lpr, pc.kpl, pc.nct, plan);
-        else plan.why = "a destination row has more than 512 links";
-        rc = upload_level(csrs[i], plan, h->levels[i]);
+        rc = upload_level(csrs[i], plans[i], h->levels[i]);
         if (rc) { smm_destroy(h); return rc; }
         csrs[i] = HostCsr{};
+        plans[i] = HostPlan{};
     }
     *out = h;
     return SMM_OK;
@@ -652,8 +671,8 @@ int smm_get_info(const smm_handle *h, int32_t level, smm_info *out)
     out->n_tiles = L.ntiles; out->max_row_nnz = L.max_row_nnz;
     out->max_tile_segments = L.max_segs; out->max_tile_elems = L.max_elems;
     out->consumer_threads = L.nct;
-    out->rows_reordered = L.reordered ? 1 : 0;
-    out->packed_rows = L.packed ? 1 : 0;
+    out->rows_reordered = (L.staged && L.reordered) ? 1 : 0;
+    out->packed_rows = (L.staged && L.packed) ? 1 : 0;
     out->sum_tile_elems = L.sum_elems; out->touched_src = L.touched;
     out->device_bytes = L.device_bytes;
     return SMM_OK;
@@ -838,10 +857,10 @@ int smm_host_plan_build(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t
     {
         std::vector<HostCsr> one(1);
         one[0] = std::move(p->csr);
-        const PlanChoice pc = choose_plan(one, n_dst, 148);
+        std::vector<HostPlan> plans;
+        plan_levels(one, n_dst, 148, plans);
         p->csr = std::move(one[0]);
-        if (pc.cfg) build_plan(p->csr, pc.packed ? -1 : 0, 0, pc.nct, p->plan);
-        else p->plan.why = "a destination row has more than 512 links";
+        p->plan = std::move(plans[0]);
     }
     *out = p;
     return SMM_OK;
@@ -861,8 +880,8 @@ int smm_host_plan_info(const smm_host_plan *p, smm_info *out, int64_t *n_segs_ou
     out->max_row_nnz = p->csr.max_row_nnz;
     out->max_tile_segments = p->plan.max_tile_segments;
     out->consumer_threads = p->plan.nct;
-    out->rows_reordered = p->plan.reordered ? 1 : 0;
-    out->packed_rows = p->plan.packed ? 1 : 0;
+    out->rows_reordered = (p->plan.ok && p->plan.reordered) ? 1 : 0;
+    out->packed_rows = (p->plan.ok && p->plan.packed) ? 1 : 0;
     out->max_tile_elems = p->plan.max_tile_elems;
     out->sum_tile_elems = p->plan.sum_tile_elems;
     out->touched_src = p->csr.touched_src;
@@ -891,14 +910,14 @@ int smm_host_plan_copy(const smm_host_plan *p, int32_t *rowptr, int32_t *col, do
 int smm_host_plan_rowmap(const smm_host_plan *p, int32_t *rowmap)
 {
     if (!p || !rowmap) return fail(SMM_ERR_INVALID, "null argument");
-    if (!p->plan.rowmap.empty()) std::memcpy(rowmap, p->plan.rowmap.data(), p->plan.rowmap.size() * sizeof(int32_t));
+    if (p->plan.ok && !p->plan.rowmap.empty()) std::memcpy(rowmap, p->plan.rowmap.data(), p->plan.rowmap.size() * sizeof(int32_t));
     return SMM_OK;
 }
 
 int smm_host_plan_rowslot(const smm_host_plan *p, int32_t *rowslot)
 {
     if (!p || !rowslot) return fail(SMM_ERR_INVALID, "null argument");
-    if (!p->plan.rowslot.empty()) std::memcpy(rowslot, p->plan.rowslot.data(), p->plan.rowslot.size() * sizeof(int32_t));
+    if (p->plan.ok && !p->plan.rowslot.empty()) std::memcpy(rowslot, p->plan.rowslot.data(), p->plan.rowslot.size() * sizeof(int32_t));
     return SMM_OK;
 }
 

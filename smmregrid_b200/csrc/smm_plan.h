@@ -58,9 +58,9 @@ bool choose_lanes(int32_t max_row_nnz, int32_t &lpr, int32_t &kpl);
 void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, HostPlan &plan);
 
 // Packed-rows layout (one thread owns up to 4 short rows): link slots it would spend on `csr`
-// (-1: a row does not fit) and whether that beats `rows` lane-per-row rows of `kpl` slots.
+// (-1: a row does not fit), and whether to use it.
 int64_t packed_slots(const HostCsr &csr);
-bool prefer_packed(int64_t slots_packed, int64_t rows, int32_t lpr, int32_t kpl);
+bool prefer_packed(int64_t slots_packed);
 
 // Consumer threads per CTA for a weight set: 512 (one CTA per SM, tiles twice as long, longer TMA
 // segments: +4 % on C4, +5 % on C2) when that still leaves at least one tile per SM, else 256.

@@ -334,7 +334,7 @@ def test_healpix_nested_reordered_plan(smm_lib, oracle, cuda, k):
     h = _create(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
     try:
         info = _info(smm_lib, h)
-        assert info["kernel_name"] == "staged" and info["rows_reordered"] == 1
+        assert info["kernel_name"] == "staged" and (info["rows_reordered"] == 1 or info["packed_rows"] == 1)
         for kernel in (0, 2):
             y = _apply(smm_lib, h, x, n_dst, np.float64, True, 0.5, imask, frac, kernel)
             assert_parity(y, y_ref, RTOL_F64, f"healpix k={k} kernel={kernel}")

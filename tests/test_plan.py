@@ -40,7 +40,7 @@ class HostPlan:
                                           self.tiles.ctypes.data, self.segs.ctypes.data,
                                           self.wplan.ctypes.data, self.iplan.ctypes.data))
         self.rowmap = None
-        if inf.rows_reordered:
+        if inf.rows_reordered and not inf.packed_rows:      # packed plans carry the rows in rowslot
             self.rowmap = np.empty(n_dst, np.int32)
             _lib.check(lib.smm_host_plan_rowmap(h, self.rowmap.ctypes.data))
         self.rowslot = None
@@ -120,12 +120,13 @@ def test_plan_emulation_matches_oracle(smm_lib, oracle, nnz_per_row):
 
 def test_plan_named_configs(smm_lib, oracle):
     from smmregrid_b200 import synth
-    for cfg, scale, lanes in (("C1", 1, (1, 4)), ("C2", 4, (2, 14)), ("C4", 5, (8, 14))):
+    for cfg, scale, lanes in (("C1", 1, (1, 16)), ("C2", 4, (2, 14)), ("C4", 5, (8, 14))):
         w = synth.config_weights(cfg, scale)
         n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
         p = HostPlan(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
         assert p.info["kernel_name"] == "staged"
         assert (p.info["lanes_per_row"], p.info["links_per_lane"]) == lanes
+        assert p.info["packed_rows"] == (cfg == "C1")        # rows of <= 16 links pack 4 to a thread
         assert p.info["touched_src"] == n_src
         if cfg != "C1":                                      # down-sampling: little over-read of the slab
             assert p.info["sum_tile_elems"] < 1.3 * n_src
@@ -180,18 +181,25 @@ def test_address_range_errors(smm_lib):
         assert b"outside the grids" in smm_lib.smm_last_error()
 
 
-def test_healpix_nested_source_gets_reordered_plan(smm_lib, oracle):
+@pytest.mark.parametrize("packed", ["0", None])
+def test_healpix_nested_source_gets_reordered_plan(smm_lib, oracle, monkeypatch, packed):
     """A HEALPix-nested source is scattered along destination rows but compact in 2-D: the
-    natural plan is rejected, the plan on rows re-ordered by mean source address is staged."""
+    natural lane-per-row plan is rejected, the plan on rows re-ordered by mean source address is
+    staged.  (The default packed layout tiles 4x the rows and may get by in natural order.)"""
     from smmregrid_b200 import synth
+    if packed is not None:
+        monkeypatch.setenv("SMM_PACKED", packed)
     for k in (1, 4):
         w = synth.healpix_weights(64, 180, 90, k)
         n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
         # nearest-neighbour sanity: every pixel index valid, poles map to the polar faces
         assert w["src_address"].min() >= 1 and w["src_address"].max() <= n_src
         p = HostPlan(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
-        assert p.info["kernel_name"] == "staged" and p.info["rows_reordered"] == 1, p.info
-        assert sorted(p.rowmap.tolist()) == list(range(n_dst))
+        assert p.info["kernel_name"] == "staged", p.info
+        assert p.info["packed_rows"] == (packed is None)
+        assert p.info["rows_reordered"] == 1 or packed is None, p.info
+        rows = p.rowslot[p.rowslot >= 0] if p.info["packed_rows"] else p.rowmap
+        assert sorted(rows.tolist()) == list(range(n_dst))
         t, sg = p.tiles, p.segs
         assert t[:, 1].sum() == n_dst and (sg[:, 0] % 8 == 0).all()
         x = np.random.default_rng(k).standard_normal((3, n_src)) + 5
@@ -241,9 +249,18 @@ def test_packed_rows_plan(smm_lib, oracle, reorder):
     assert_parity(p.emulate(x), oracle.apply_weights_c(x, mat, None, None, 0.0, False), 1e-12)
 
 
-def test_packed_rows_not_used_for_uniform_rows(smm_lib):
-    from smmregrid_b200 import synth
-    w = synth.config_weights("C1", 1)                    # bilinear: 4 links in every row, nothing to pack
-    p = HostPlan(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"],
-                 w.sizes["src_grid_size"], w.sizes["dst_grid_size"])
-    assert p.info["packed_rows"] == 0 and (p.info["lanes_per_row"], p.info["links_per_lane"]) == (1, 4)
+def test_packed_rows_fall_back_when_footprint_too_large(smm_lib, oracle):
+    """A packed tile holds 4x the rows; when its source footprint does not fit the stages the
+    lane-per-row layout (smaller tiles) is used instead."""
+    rng = np.random.default_rng(3)
+    n_dst, k = 2048, 4
+    n_src = n_dst * 40                                   # 40 source columns per destination row
+    dst = np.repeat(np.arange(n_dst), k)
+    src = dst * 40 + rng.integers(0, 40, size=dst.size)   # every tile row touches its own 40-column block
+    w = rng.random((dst.size, 1))
+    p = HostPlan(smm_lib, src + 1, dst + 1, w, n_src, n_dst)
+    assert p.info["kernel_name"] == "staged" and p.info["packed_rows"] == 0, p.info
+    assert p.info["max_tile_elems"] <= 25600
+    mat = oracle.compute_weights_matrix_c(src + 1, dst + 1, w, n_src, n_dst)
+    x = rng.standard_normal((2, n_src))
+    assert_parity(p.emulate(x), oracle.apply_weights_c(x, mat, None, None, 0.0, False), 1e-12)
