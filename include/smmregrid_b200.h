@@ -166,6 +166,17 @@ int smm_apply_levels_host(const smm_handle *h, int32_t n_sel, const int32_t *lev
                           const uint8_t *masked, double remap_area_min, int64_t chunk_rows);
 
 /*
+ * detect_nan_variation_dims (smmregrid/util.py:57-85), one axis per call: the DEVICE array x is
+ * viewed as [outer, n_axis, inner] (contiguous); *count_out = number of (outer, inner)
+ * positions whose NaN-ness changes somewhere along the axis -- the reference's
+ * `isnull().astype("int8").diff(dim).astype(bool).any(dim).sum()`.  A dimension "has NaN
+ * variation" (and becomes a mask dimension, regrid.py:630-653) when the count is > 0.
+ * NaN only, as isnull: +-inf does not count.  Synchronous on `stream`.
+ */
+int smm_nan_variation(const void *x, int32_t x_dtype, int64_t outer, int64_t n_axis, int64_t inner,
+                      int64_t *count_out, smm_stream_t stream);
+
+/*
  * Host-only introspection of the operator construction (no device needed): builds the
  * same CSR + tile plan smm_create uploads, so the host logic can be verified on a CPU-only
  * machine.  No compute entry point exists on the host side.

@@ -280,3 +280,29 @@ def apply_weights_renorm_np(x, mat: CooMatrix, dst_imask=None, dst_frac=None, re
     if remap_area_min > 0.0:
         y = np.where(np.broadcast_to(dst_frac, y.shape) < remap_area_min, np.nan, y)
     return y.reshape(kept + (mat.shape[1],))
+
+
+def nan_variation_count_np(field, axis):
+    """util.py:75-78: `nan_mask.astype("int8").diff(dim).astype(bool).any(dim).sum()`."""
+    nan_mask = np.isnan(np.asarray(field))
+    if nan_mask.shape[axis] < 2:
+        return 0
+    return int(np.diff(nan_mask.astype(np.int8), axis=axis).astype(bool).any(axis=axis).sum())
+
+
+def detect_nan_variation_dims_np(field, time_axis, check_axes):
+    """util.py:57-85 on a bare array: drop the time axis at its first step (util.py:69-71), then
+    report the members of check_axes (numbered on the ORIGINAL array) with count > 0."""
+    field = np.asarray(field)
+    out = []
+    if time_axis is not None:
+        field = np.take(field, 0, axis=time_axis)
+    for d in check_axes:
+        ax = d
+        if time_axis is not None:
+            if d == time_axis:
+                continue
+            ax = d - (d > time_axis)
+        if nan_variation_count_np(field, ax) > 0:
+            out.append(d)
+    return out

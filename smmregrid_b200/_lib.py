@@ -47,6 +47,7 @@ SIGNATURES = {
     "smm_apply_levels": (ctypes.c_int, [vp, i32, vp, vp, i32, i64, i64, i64, vp, i32, i64, i64, vp, f64, vp]),
     "smm_apply_host": (ctypes.c_int, [vp, i32, vp, i32, i64, i64, vp, i32, i64, i32, f64, i64]),
     "smm_apply_levels_host": (ctypes.c_int, [vp, i32, vp, vp, i32, i64, vp, i32, vp, f64, i64]),
+    "smm_nan_variation": (ctypes.c_int, [vp, i32, i64, i64, i64, P(i64), vp]),
     "smm_host_plan_build": (ctypes.c_int, [i64, i64, i64, vp, vp, vp, i32, i32, P(vp)]),
     "smm_host_plan_info": (ctypes.c_int, [vp, P(SmmInfo), P(i64)]),
     "smm_host_plan_copy": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -711,6 +711,39 @@ int smm_mask_sum(smm_handle *h, int32_t level, const int32_t *src_imask, int32_t
     return SMM_OK;
 }
 
+int smm_nan_variation(const void *x, int32_t x_dtype, int64_t outer, int64_t n_axis, int64_t inner,
+                      int64_t *count_out, smm_stream_t stream)
+{
+    if (!count_out) return fail(SMM_ERR_INVALID, "null count_out");
+    *count_out = 0;
+    if (x_dtype != SMM_F32 && x_dtype != SMM_F64) return fail(SMM_ERR_DTYPE, "x_dtype must be SMM_F32 or SMM_F64");
+    if (outer < 0 || n_axis < 0 || inner < 0) return fail(SMM_ERR_INVALID, "negative extent");
+    const int64_t npos = outer * inner;
+    if (npos == 0 || n_axis < 2) return SMM_OK;
+    if (!x) return fail(SMM_ERR_INVALID, "null x");
+    if ((npos + 255) / 256 > INT32_MAX) return fail(SMM_ERR_INVALID, "too many positions for one launch");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long *d_count = nullptr;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_count), sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st);
+    if (e == cudaSuccess) {
+        const unsigned grid = static_cast<unsigned>((npos + 255) / 256);
+        if (x_dtype == SMM_F32)
+            nan_variation_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(x), outer, n_axis, inner, d_count);
+        else
+            nan_variation_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double *>(x), outer, n_axis, inner, d_count);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    unsigned long long host = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&host, d_count, sizeof(host), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_count);
+    if (e != cudaSuccess) return fail(SMM_ERR_CUDA, std::string("smm_nan_variation: ") + cudaGetErrorString(e));
+    *count_out = static_cast<int64_t>(host);
+    return SMM_OK;
+}
+
 int smm_set_dst_mask(smm_handle *h, int32_t level, const int32_t *dst_grid_imask, const double *dst_grid_frac)
 {
     int rc = check_level(h, level);

@@ -167,5 +167,41 @@ def main():
     case_3d("ocean3d_f32", w, x)
 
 
+def nan_variation_cases():
+    """detect_nan_variation_dims (smmregrid/util.py:57-85), the reference's own function, on
+    fields whose missing-value pattern varies along none / one / two of the extra dimensions."""
+    from smmregrid.util import detect_nan_variation_dims as ref_detect
+    rng = np.random.default_rng(77)
+    dims = ("time", "lev", "member", "lat", "lon")
+    out = {}
+    for i, dt in enumerate((np.float32, np.float64)):
+        base = rng.standard_normal((3, 5, 2, 6, 8)).astype(dt)
+        fields = {}
+        f = base.copy(); f[:, :, :, 2:4, 3:6] = np.nan                      # static land: no variation
+        fields["static"] = f
+        f = base.copy()
+        for lev in range(5):                                                   # bathymetry: varies along lev only
+            f[:, lev, :, :lev + 1, :] = np.nan
+        fields["lev"] = f
+        f = fields["lev"].copy(); f[:, :, 1, 5, 7] = np.nan                 # ... and one member differs
+        fields["lev_member"] = f
+        f = base.copy(); f[1:, 2, 0, 0, 0] = np.nan                          # only later time steps: first step clean
+        fields["later_steps_only"] = f
+        f = base.copy(); f[:, 3, :, 1, 1] = np.inf                           # inf is not null
+        fields["inf_only"] = f
+        for name, f in fields.items():
+            da = xr.DataArray(f, dims=dims)
+            got = ref_detect(da, time_dim=["time"], check_dims=["lev", "member"])
+            out[f"{name}_{np.dtype(dt).name}"] = f
+            out[f"{name}_{np.dtype(dt).name}_dims"] = np.array([dims.index(d) for d in got], np.int64)
+            # no time dimension present: the whole field is inspected
+            got2 = ref_detect(xr.DataArray(f[0], dims=dims[1:]), time_dim=["time"], check_dims=["lev", "member"])
+            assert got2 == got
+    np.savez_compressed(os.path.join(HERE, "nan_variation.npz"), **out)
+    print("nan_variation.npz:", {k: v.tolist() for k, v in out.items() if k.endswith("_dims")})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] != "nanvar":
+        main()
+    nan_variation_cases()

@@ -146,7 +146,15 @@ class DataArray:
     def mean(self, dim=None): return self._reduce(np.mean, dim)
     def all(self, dim=None): return self._reduce(np.all, dim)
 
+    # the surface util.py:detect_nan_variation_dims uses (util.py:69-80)
+    def isnull(self): return self._new(np.isnan(self.data))
+    def astype(self, dt): return self._new(self.data.astype(dt))
+    def diff(self, dim): return self._new(np.diff(self.data, axis=self.dims.index(dim)))
+    def any(self, dim=None): return self._reduce(np.any, dim)
+    def sum(self, dim=None): return self._reduce(np.sum, dim)
+
     def isel(self, indexers=None, **kw):
+        kw.pop("drop", None)
         indexers = dict(indexers or {}, **kw)
         key = tuple(indexers.get(d, slice(None)) for d in self.dims)
         dims = [d for d in self.dims if not isinstance(indexers.get(d, slice(None)), (int, np.integer))]

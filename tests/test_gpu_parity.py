@@ -615,3 +615,28 @@ def test_packed_rows_threshold_replay_and_renorm(smm_lib, oracle, cuda):
         assert_parity(_apply(smm_lib, h, x, n_dst, np.float64, False, 0.0), y_ref, RTOL_F64, "back to reference mode")
     finally:
         smm_lib.smm_destroy(h)
+
+
+def test_nan_variation_probe(smm_lib, oracle, cuda):
+    """detect_nan_variation_dims on the device against the reference-made fixture and the oracle."""
+    import os
+    import torch
+    from smmregrid_b200 import detect_nan_variation_dims
+    from smmregrid_b200.util import nan_variation_count
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nan_variation.npz"))
+    for k in [k for k in g.files if not k.endswith("_dims")]:
+        want = g[k + "_dims"].tolist()
+        assert detect_nan_variation_dims(g[k], 0, [1, 2]) == want, k
+        assert detect_nan_variation_dims(g[k], [0], [1, 2]) == want, k            # the reference passes a list
+        assert detect_nan_variation_dims(torch.from_numpy(g[k]).cuda(), 0, [1, 2]) == want, k
+        assert detect_nan_variation_dims(g[k][0], None, [0, 1]) == [d - 1 for d in want], k
+    # counts, every axis, odd sizes, against the oracle
+    rng = np.random.default_rng(8)
+    for dt in (np.float32, np.float64):
+        f = rng.standard_normal((3, 7, 33, 5)).astype(dt)
+        f[rng.random(f.shape) < 0.05] = np.nan
+        f[0, 0, 0, 0] = np.inf
+        for ax in range(4):
+            assert nan_variation_count(f, ax) == oracle.nan_variation_count_np(f, ax), (dt, ax)
+    assert nan_variation_count(np.zeros((4, 1, 3), np.float32), 1) == 0           # nothing to diff
+    assert nan_variation_count(np.arange(12).reshape(3, 4), 0) == 0               # integers have no NaN

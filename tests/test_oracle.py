@@ -149,3 +149,15 @@ def test_out_of_range_addresses(oracle):
             fn(np.array([0]), np.array([1]), np.ones((1, 1)), 4, 4)
         with pytest.raises(ValueError):
             fn(np.array([1]), np.array([5]), np.ones((1, 1)), 4, 4)
+
+
+def test_nan_variation_oracle_matches_reference_fixture(oracle):
+    """detect_nan_variation_dims: fixture produced by the reference's own util.py function."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nan_variation.npz"))
+    names = [k for k in g.files if not k.endswith("_dims")]
+    assert len(names) == 10
+    for k in names:
+        want = g[k + "_dims"].tolist()
+        assert oracle.detect_nan_variation_dims_np(g[k], 0, [1, 2]) == want, k
+        assert oracle.detect_nan_variation_dims_np(g[k][0], None, [0, 1]) == [d - 1 for d in want], k
