@@ -221,6 +221,13 @@ def run_3d(args, rg, w, T, xdt, ydt, sx, sy, area_min, dev, g, world, rank, desc
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = abytes / (ms * 1e-3) / 1e9
+    traffic = None            # per launch, from the committed ncu capture of this configuration
+    try:
+        for t in json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["captures"]:
+            if (t["workload"], t["batch_rows"], t["x_dtype"], t["y_dtype"]) == (args.workload, T, args.xdtype, args.ydtype):
+                traffic = t["dram_bytes_per_launch"]
+    except Exception:
+        pass
     print(json.dumps({
         "metric": METRIC, "value": T * L * n_src / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -229,7 +236,7 @@ def run_3d(args, rg, w, T, xdt, ydt, sx, sy, area_min, dev, g, world, rank, desc
                    "kernels": sorted({i["kernel_name"] for i in infos}), "lanes_per_row": infos[0]["lanes_per_row"],
                    "nan_cells": int(torch.isnan(y).sum().item()), "x_dtype": args.xdtype, "y_dtype": args.ydtype},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "algorithmic_bytes_per_launch": abytes},
+                     "traffic": traffic, "algorithmic_bytes_per_launch": abytes},
         "gpu_launches": int(lib.smm_launch_count() - l0)}), flush=True)
 
 
