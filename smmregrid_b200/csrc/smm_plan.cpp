@@ -261,13 +261,7 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
         out.sum_elems += off;
         if (off > 65535u) { out.too_big = true; return; }
 
-        // Register image.  A row's links may sit in any (lane, slot) of the row's lane group --
-        // the kernel sums them all -- so the assignment is chosen to spread each warp-wide
-        // shared-memory load over distinct banks: per warp and per slot, a bipartite matching
-        // of lanes to banks (4-byte elements: bank = local index % 32) over the links each
-        // lane's row still has to place.  Unplaced slots carry weight 0 and re-read the row's
-        // first link (the fast path skips the non-finite test, so a padded slot must never see
-        // a NaN the row does not own).
+        // ---- register image of the tile: which (thread, slot) holds which link
         const Seg *sb = out.segs.data() + td.seg0;
         const size_t tbase = static_cast<size_t>(t) * kpl * nct;
         auto local_index = [&](uint32_t c) -> uint32_t {      // footprint-local element of source column c
@@ -278,73 +272,77 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
             }
             return sb[lo].dst + (c - sb[lo].src);
         };
-        if (packed) {
-            // rows in order, each into its 1-4 sub-rows; padding slots (weight 0) re-read a link of
-            // the row that owns the sub-row, empty sub-rows a link of the thread's first row
-            const size_t sbase = static_cast<size_t>(t) * kSubRows * nct;
-            std::vector<int32_t> thread_first(static_cast<size_t>(nct), -1);
-            for (int64_t pos = r0; pos < r1; ++pos) {
-                const int64_t r = row_at(pos);
-                const int32_t thread = row_thread[pos], u0 = row_sub[pos];
-                const int32_t a = csr.rowptr[r], b = csr.rowptr[r + 1];
-                const int32_t c = std::max(1, (b - a + kSubLinks - 1) / kSubLinks);
-                plan.rowslot[sbase + static_cast<size_t>(u0) * nct + thread] = static_cast<int32_t>(r);
-                for (int32_t u = 1; u < c; ++u) plan.rowslot[sbase + static_cast<size_t>(u0 + u) * nct + thread] = -2;
-                uint16_t first_li = 0;
-                for (int32_t j = a; j < b; ++j) {
-                    const uint32_t li = local_index(static_cast<uint32_t>(csr.col[j]));
-                    const int32_t k = u0 * kSubLinks + (j - a);
-                    plan.wplan[tbase + static_cast<size_t>(k) * nct + thread] = csr.val[j];
-                    plan.iplan[tbase + static_cast<size_t>(k) * nct + thread] = static_cast<uint16_t>(li);
-                    if (j == a) first_li = static_cast<uint16_t>(li);
-                }
-                if (b > a && thread_first[thread] < 0) thread_first[thread] = first_li;
-                for (int32_t k = u0 * kSubLinks + (b - a); k < (u0 + c) * kSubLinks; ++k)
-                    plan.iplan[tbase + static_cast<size_t>(k) * nct + thread] = first_li;
-            }
-            for (int32_t thread = 0; thread < nct; ++thread) {
-                if (thread_first[thread] < 0) continue;
-                for (int32_t u = 0; u < kSubRows; ++u)
-                    if (plan.rowslot[sbase + static_cast<size_t>(u) * nct + thread] == -1)
-                        for (int32_t k = u * kSubLinks; k < (u + 1) * kSubLinks; ++k)
-                            plan.iplan[tbase + static_cast<size_t>(k) * nct + thread] = static_cast<uint16_t>(thread_first[thread]);
-            }
-            continue;
-        }
-        const int rows_per_warp = 32 / lpr;
-        const int nwarps = nct / 32;
+        // Link placement for one warp: lane `l` serves row slot l / lpr_ of the warp; the links of a
+        // row slot wait in bucket[slot * 32 + bank] (bank = local index % 32 for 4-byte elements).
+        // A row's links may sit in any (lane, slot) of its lane group -- the kernel sums them
+        // all -- so per link slot a bipartite matching of lanes to banks spreads the warp-wide
+        // shared-memory load over distinct banks.  Unplaced slots carry weight 0.
         struct Link { uint16_t li; double w; };
-        std::vector<std::vector<Link>> bucket(static_cast<size_t>(rows_per_warp) * 32);
-        for (int wi = 0; wi < nwarps; ++wi) {
-            uint16_t first_li[32] = {0};
-            int remaining[32] = {0};
-            int32_t rep[32][32];                         // one link of the row per bank, for padding
-            for (auto &rr : rep) for (int32_t &v : rr) v = -1;
-            for (auto &b : bucket) b.clear();
-            for (int jr = 0; jr < rows_per_warp; ++jr) {
-                const int64_t pos = r0 + static_cast<int64_t>(wi) * rows_per_warp + jr;
-                if (pos >= r1) continue;
-                const int64_t r = row_at(pos);
-                const int32_t a = csr.rowptr[r], b = csr.rowptr[r + 1];
-                for (int32_t j = b - 1; j >= a; --j) {          // pushed in reverse: popped ascending
-                    const uint32_t c = static_cast<uint32_t>(csr.col[j]);
-                    int lo = 0, hi = td.nseg - 1;                 // last segment with src <= c
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) >> 1;
-                        if (sb[mid].src <= c) lo = mid; else hi = mid - 1;
-                    }
-                    const uint32_t li = sb[lo].dst + (c - sb[lo].src);
-                    bucket[static_cast<size_t>(jr) * 32 + (li & 31u)].push_back(Link{static_cast<uint16_t>(li), csr.val[j]});
-                    rep[jr][li & 31u] = static_cast<int32_t>(li);
-                    if (j == a) first_li[jr] = static_cast<uint16_t>(li);
-                }
-                remaining[jr] = b - a;
+        std::vector<std::vector<Link>> bucket(32 * 32);
+        int remaining[32];
+        int32_t rep_any[32];                         // some link of the row slot (padding when a slot places nothing)
+        auto reset_warp = [&]() {
+            for (auto &bk : bucket) bk.clear();
+            for (int i = 0; i < 32; ++i) { rep_any[i] = -1; remaining[i] = 0; }
+        };
+        auto add_link = [&](int slot, uint32_t li, double w) {
+            bucket[static_cast<size_t>(slot) * 32 + (li & 31u)].push_back(Link{static_cast<uint16_t>(li), w});
+            rep_any[slot] = static_cast<int32_t>(li);
+            ++remaining[slot];
+        };
+        std::vector<Link> pool[32];                  // a row slot's links in ascending-src order
+        // [nslots][32] candidate placements: in order / bank-matched / bank-matched + co-scheduled
+        std::vector<uint16_t> s_li, m_li, c_li;
+        std::vector<double> s_w, m_w, c_w;
+        std::vector<uint8_t> s_have, m_have, c_have;
+        // shared-memory wavefronts of a placement: per slot, the fullest bank counted in DISTINCT
+        // addresses (lanes reading the same word are served by one broadcast)
+        auto wavefronts = [&](const std::vector<uint16_t> &li, int nslots) -> int {
+            int total = 0;
+            for (int k = 0; k < nslots; ++k) {
+                uint16_t a[32];
+                std::copy(li.begin() + k * 32, li.begin() + k * 32 + 32, a);
+                std::sort(a, a + 32);
+                int cnt[32] = {0}, worst = 0;
+                for (int i = 0; i < 32; ++i)
+                    if (i == 0 || a[i] != a[i - 1]) worst = std::max(worst, ++cnt[a[i] & 31]);
+                total += worst;
             }
-            for (int k = 0; k < kpl; ++k) {
+            return total;
+        };
+        auto place_warp = [&](int lpr_, int nslots, int slot0, int thread0) -> bool {
+            const int rows_in_warp = 32 / lpr_;
+            const size_t cells = static_cast<size_t>(nslots) * 32;
+            s_li.assign(cells, 0); m_li.assign(cells, 0); c_li.assign(cells, 0);
+            s_w.assign(cells, 0.0); m_w.assign(cells, 0.0); c_w.assign(cells, 0.0);
+            s_have.assign(cells, 0); m_have.assign(cells, 0); c_have.assign(cells, 0);
+            // in-order alternative: link j of a row slot -> (lane j % lpr_, slot j / lpr_).  It keeps
+            // equal addresses of neighbouring rows in the same slot (up-sampling: broadcasts), which
+            // the bank matching below cannot see
+            for (int jr = 0; jr < rows_in_warp; ++jr) {
+                pool[jr].clear();
+                for (int b = 0; b < 32; ++b)
+                    for (const Link &l : bucket[static_cast<size_t>(jr) * 32 + b]) pool[jr].push_back(l);
+                std::sort(pool[jr].begin(), pool[jr].end(), [](const Link &x, const Link &y) { return x.li < y.li; });
+                for (size_t j = 0; j < pool[jr].size(); ++j) {
+                    const size_t at = (j / lpr_) * 32 + static_cast<size_t>(jr) * lpr_ + j % lpr_;
+                    s_li[at] = pool[jr][j].li; s_w[at] = pool[jr][j].w; s_have[at] = 1;
+                }
+            }
+            auto run_matching = [&](bool cosched, std::vector<uint16_t> &o_li, std::vector<double> &o_w,
+                                    std::vector<uint8_t> &o_have) -> bool {
+            // (re)fill the per-bank buckets from the row pools; descending, so pop_back ascends
+            for (auto &bk : bucket) bk.clear();
+            for (int jr = 0; jr < rows_in_warp; ++jr) {
+                remaining[jr] = static_cast<int>(pool[jr].size());
+                for (size_t j = pool[jr].size(); j-- > 0;)
+                    bucket[static_cast<size_t>(jr) * 32 + (pool[jr][j].li & 31u)].push_back(pool[jr][j]);
+            }
+            for (int k = 0; k < nslots; ++k) {
                 uint32_t cand[32];
                 int order[32], ncand[32];
                 for (int lane = 0; lane < 32; ++lane) {
-                    const int jr = lane / lpr;
+                    const int jr = lane / lpr_;
                     uint32_t m = 0;
                     for (int b = 0; b < 32; ++b)
                         if (!bucket[static_cast<size_t>(jr) * 32 + b].empty()) m |= 1u << b;
@@ -359,12 +357,24 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
                 // a lane may only be matched while its row still has links left for this slot:
                 // a row with fewer remaining links than lanes matches only that many lanes
                 int quota[32];
-                for (int jr = 0; jr < rows_per_warp; ++jr) quota[jr] = remaining[jr];
+                for (int jr = 0; jr < rows_in_warp; ++jr) quota[jr] = remaining[jr];
+                // banks are tried fullest first, so a row drains its banks evenly and the later
+                // slots still have a choice
+                uint8_t pref[32][32];
+                for (int jr = 0; jr < rows_in_warp; ++jr) {
+                    uint8_t *pr = pref[jr];
+                    for (int b = 0; b < 32; ++b) pr[b] = static_cast<uint8_t>(b);
+                    const size_t base = static_cast<size_t>(jr) * 32;
+                    std::stable_sort(pr, pr + 32, [&](uint8_t x, uint8_t y) {
+                        return bucket[base + x].size() > bucket[base + y].size();
+                    });
+                }
                 auto augment = [&](auto &&self, int lane, uint32_t &seen) -> bool {
-                    uint32_t m = cand[lane] & ~seen;
-                    while (m) {
-                        const int b = __builtin_ctz(m);
-                        m &= m - 1;
+                    const uint8_t *pr = pref[lane / lpr_];
+                    for (int i = 0; i < 32; ++i) {
+                        const int b = pr[i];
+                        if (!((cand[lane] >> b) & 1u)) break;          // sorted by size: the rest is empty
+                        if ((seen >> b) & 1u) continue;
                         seen |= 1u << b;
                         if (owner[b] < 0 || self(self, owner[b], seen)) { owner[b] = lane; return true; }
                     }
@@ -373,7 +383,7 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
                 bool matched[32] = {false};
                 for (int oi = 0; oi < 32; ++oi) {
                     const int lane = order[oi];
-                    const int jr = lane / lpr;
+                    const int jr = lane / lpr_;
                     if (quota[jr] <= 0 || cand[lane] == 0) continue;
                     uint32_t seen = 0;
                     if (augment(augment, lane, seen)) { matched[lane] = true; --quota[jr]; }
@@ -386,7 +396,7 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
                 bool have[32] = {false};
                 for (int lane = 0; lane < 32; ++lane) {
                     if (!matched[lane] || lane_bank[lane] < 0) continue;
-                    const int jr = lane / lpr;
+                    const int jr = lane / lpr_;
                     auto &bk = bucket[static_cast<size_t>(jr) * 32 + lane_bank[lane]];
                     if (bk.empty()) continue;            // bank taken by a same-row lane in a previous augmentation
                     chosen[lane] = bk.back(); bk.pop_back(); have[lane] = true;
@@ -394,7 +404,7 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
                 }
                 for (int lane = 0; lane < 32; ++lane) {
                     if (have[lane]) continue;
-                    const int jr = lane / lpr;
+                    const int jr = lane / lpr_;
                     if (remaining[jr] <= 0) continue;
                     int best = -1;
                     for (int b = 0; b < 32; ++b)
@@ -403,27 +413,133 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
                     chosen[lane] = bk.back(); bk.pop_back(); have[lane] = true;
                     --remaining[jr]; ++load[best];
                 }
-                for (int lane = 0; lane < 32; ++lane) {
-                    const int thread = wi * 32 + lane;
-                    const size_t at = tbase + static_cast<size_t>(k) * nct + thread;
-                    if (have[lane]) {
-                        plan.wplan[at] = chosen[lane].w;
-                        plan.iplan[at] = chosen[lane].li;
-                    } else {
-                        // padding: weight 0 on one of the row's own links, in a bank this slot
-                        // does not use yet when the row has one there
-                        const int jr = lane / lpr;
+                // Co-scheduling: neighbouring rows often link the SAME source element (the shared
+                // boundary column of two conservative cells, the common corner of bilinear cells).
+                // Lanes reading one address are served by one broadcast, but only if they read it
+                // in the same slot -- so whenever a lane takes an address that another row of the
+                // warp also has, a lane of that row takes it now as well (its previous pick goes
+                // back to its bucket).  Without this the twins are consumed at different times and
+                // pile up in a few banks in the last slots.
+                bool locked[32] = {false};
+                for (int lane = 0; cosched && lane < 32; ++lane) {
+                    if (!have[lane] || locked[lane]) continue;
+                    const uint16_t a = chosen[lane].li;
+                    const int b = a & 31, jr0 = lane / lpr_;
+                    for (int jr = 0; jr < rows_in_warp; ++jr) {
+                        if (jr == jr0) continue;
+                        auto &bk = bucket[static_cast<size_t>(jr) * 32 + b];
+                        size_t at = bk.size();
+                        for (size_t i = 0; i < bk.size(); ++i)
+                            if (bk[i].li == a) { at = i; break; }
+                        if (at == bk.size()) continue;
                         int pick = -1;
-                        for (int b = 0; b < 32 && pick < 0; ++b)
-                            if (load[b] == 0 && rep[jr][b] >= 0) pick = b;
-                        plan.wplan[at] = 0.0;
-                        if (pick >= 0) { plan.iplan[at] = static_cast<uint16_t>(rep[jr][pick]); ++load[pick]; }
-                        else plan.iplan[at] = first_li[jr];
+                        for (int l2 = jr * lpr_; l2 < (jr + 1) * lpr_ && pick < 0; ++l2)
+                            if (!have[l2]) pick = l2;
+                        for (int l2 = jr * lpr_; l2 < (jr + 1) * lpr_ && pick < 0; ++l2)
+                            if (!locked[l2]) pick = l2;
+                        if (pick < 0) continue;
+                        const Link twin = bk[at];
+                        bk.erase(bk.begin() + static_cast<std::ptrdiff_t>(at));
+                        --remaining[jr];
+                        if (have[pick]) {
+                            bucket[static_cast<size_t>(jr) * 32 + (chosen[pick].li & 31)].push_back(chosen[pick]);
+                            ++remaining[jr];
+                        }
+                        chosen[pick] = twin; have[pick] = true;
+                        locked[pick] = locked[lane] = true;
                     }
                 }
+                for (int lane = 0; lane < 32; ++lane)
+                    if (have[lane]) {
+                        o_li[k * 32 + lane] = chosen[lane].li; o_w[k * 32 + lane] = chosen[lane].w; o_have[k * 32 + lane] = 1;
+                    }
             }
-            for (int jr = 0; jr < rows_per_warp; ++jr)
-                if (remaining[jr] != 0) { out.failed = true; return; }
+            for (int jr = 0; jr < rows_in_warp; ++jr)
+                if (remaining[jr] != 0) return false;
+            return true;
+            };
+            if (!run_matching(false, m_li, m_w, m_have) || !run_matching(true, c_li, c_w, c_have)) return false;
+            // padding (weight 0) broadcasts an address the warp reads in this slot anyway: no
+            // extra wavefront, and the value belongs to a row of this warp, whose non-finite
+            // vote is warp-wide -- a padded slot never drags in a NaN the warp does not own
+            auto pad_out = [&](std::vector<uint16_t> &li, const std::vector<uint8_t> &hv) {
+                for (int k = 0; k < nslots; ++k) {
+                    int32_t pad = -1;
+                    for (int lane = 0; lane < 32 && pad < 0; ++lane)
+                        if (hv[k * 32 + lane]) pad = li[k * 32 + lane];
+                    for (int lane = 0; lane < 32 && pad < 0; ++lane)
+                        if (rep_any[lane / lpr_] >= 0) pad = rep_any[lane / lpr_];
+                    if (pad < 0) pad = 0;
+                    for (int lane = 0; lane < 32; ++lane)
+                        if (!hv[k * 32 + lane]) li[k * 32 + lane] = static_cast<uint16_t>(pad);
+                }
+            };
+            pad_out(m_li, m_have);
+            pad_out(c_li, c_have);
+            pad_out(s_li, s_have);
+            const int cost_s = wavefronts(s_li, nslots), cost_m = wavefronts(m_li, nslots), cost_c = wavefronts(c_li, nslots);
+            const int pick = (cost_s <= cost_m && cost_s <= cost_c) ? 0 : (cost_m <= cost_c ? 1 : 2);
+            const std::vector<uint16_t> &li = pick == 0 ? s_li : pick == 1 ? m_li : c_li;
+            const std::vector<double> &w = pick == 0 ? s_w : pick == 1 ? m_w : c_w;
+            for (int k = 0; k < nslots; ++k)
+                for (int lane = 0; lane < 32; ++lane) {
+                    const size_t at = tbase + static_cast<size_t>(slot0 + k) * nct + thread0 + lane;
+                    plan.wplan[at] = w[k * 32 + lane];
+                    plan.iplan[at] = li[k * 32 + lane];
+                }
+            return true;
+        };
+
+        if (packed) {
+            // links j of a row go to its sub-row u0 + j / 4 (any slot of that sub-row)
+            const size_t sbase = static_cast<size_t>(t) * kSubRows * nct;
+            const int nwarps = nct / 32;
+            int64_t pos = r0;
+            for (int wi = 0; wi < nwarps; ++wi) {
+                const int64_t pos0 = pos;
+                while (pos < r1 && row_thread[pos] / 32 == wi) ++pos;
+                int32_t thread_first[32];
+                for (int32_t &v : thread_first) v = -1;
+                for (int64_t q = pos0; q < pos; ++q) {
+                    const int64_t r = row_at(q);
+                    const int32_t thread = row_thread[q], u0 = row_sub[q];
+                    const int32_t a = csr.rowptr[r], b = csr.rowptr[r + 1];
+                    const int32_t c = std::max(1, (b - a + kSubLinks - 1) / kSubLinks);
+                    plan.rowslot[sbase + static_cast<size_t>(u0) * nct + thread] = static_cast<int32_t>(r);
+                    for (int32_t u = 1; u < c; ++u) plan.rowslot[sbase + static_cast<size_t>(u0 + u) * nct + thread] = -2;
+                    if (b > a && thread_first[thread & 31] < 0)
+                        thread_first[thread & 31] = static_cast<int32_t>(local_index(static_cast<uint32_t>(csr.col[a])));
+                }
+                for (int u = 0; u < kSubRows; ++u) {
+                    reset_warp();
+                    for (int lane = 0; lane < 32; ++lane) rep_any[lane] = thread_first[lane];
+                    for (int64_t q = pos0; q < pos; ++q) {
+                        const int32_t lane = row_thread[q] & 31, u0 = row_sub[q];
+                        const int64_t r = row_at(q);
+                        const int32_t a = csr.rowptr[r], b = csr.rowptr[r + 1];
+                        const int32_t j0 = a + (u - u0) * kSubLinks;
+                        if (u < u0 || j0 >= b) continue;
+                        for (int32_t j = std::min(b, j0 + kSubLinks) - 1; j >= j0; --j)
+                            add_link(lane, local_index(static_cast<uint32_t>(csr.col[j])), csr.val[j]);
+                    }
+                    if (!place_warp(1, kSubLinks, u * kSubLinks, wi * 32)) { out.failed = true; return; }
+                }
+            }
+            continue;
+        }
+        const int rows_per_warp = 32 / lpr;
+        const int nwarps = nct / 32;
+        for (int wi = 0; wi < nwarps; ++wi) {
+            reset_warp();
+            for (int jr = 0; jr < rows_per_warp; ++jr) {
+                const int64_t pos = r0 + static_cast<int64_t>(wi) * rows_per_warp + jr;
+                if (pos >= r1) continue;
+                const int64_t r = row_at(pos);
+                const int32_t a = csr.rowptr[r], b = csr.rowptr[r + 1];
+                for (int32_t j = b - 1; j >= a; --j)            // pushed in reverse: popped ascending
+                    add_link(jr, local_index(static_cast<uint32_t>(csr.col[j])), csr.val[j]);
+            }
+            if (!place_warp(lpr, kpl, 0, wi * 32)) { out.failed = true; return; }
         }
     }
     };
