@@ -397,16 +397,11 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
                         // same fast / filled / adaptive scheme as the lane-per-row consumers below
                         const bool probe = !prefer_fill || (n_done & 15u) == 0;
                         ++n_done;
-                        if (!probe) {
-                            lane_sum4<TX, true>(sb, off, w, s4);
-                        } else {
-                            prefer_fill = false;
+                        if (probe) {
                             lane_sum4<TX, false>(sb, off, w, s4);
-                            if (__any_sync(0xffffffffu, not_finite((s4[0] + s4[1]) + (s4[2] + s4[3])))) {
-                                lane_sum4<TX, true>(sb, off, w, s4);
-                                prefer_fill = true;
-                            }
+                            prefer_fill = __any_sync(0xffffffffu, not_finite((s4[0] + s4[1]) + (s4[2] + s4[3])));
                         }
+                        if (prefer_fill) lane_sum4<TX, true>(sb, off, w, s4);      // one copy of the filled sum
                     }
                     if (n == nb - 1) {
                         __syncwarp();
