@@ -88,8 +88,38 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint
 __device__ __forceinline__ float fill_invalid(float v) { return (fabsf(v) <= 3.402823466e+38f) ? v : 1e20f; }
 __device__ __forceinline__ double fill_invalid(double v) { return (fabs(v) <= 1.7976931348623157e+308) ? v : 1e20; }
 
-template <typename TX>
-__device__ __forceinline__ TX ld_nc(const TX *p) { return __ldg(p); }
+// Gather load of one source element, with the smallest L2 prefetch-size hint (SASS LDG.E.LTC64B):
+// a random 4-byte gather was measured to pull 128 bytes from DRAM without it.  B200, B = 64:
+// C5dis 5.59 -> 4.98 ms, C5nn 1.43 -> 1.29 ms; the 256-byte hint costs 7 %.  SMM_GATHER_L2 = 0
+// (no hint) | 64 | 128 | 256 at compile time.
+#ifndef SMM_GATHER_L2
+#define SMM_GATHER_L2 64
+#endif
+template <typename TX> __device__ __forceinline__ TX ld_nc(const TX *p);
+template <> __device__ __forceinline__ float ld_nc<float>(const float *p)
+{
+#if SMM_GATHER_L2 == 64
+    float v; asm volatile("ld.global.nc.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+#elif SMM_GATHER_L2 == 128
+    float v; asm volatile("ld.global.nc.L2::128B.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+#elif SMM_GATHER_L2 == 256
+    float v; asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+#else
+    return __ldg(p);
+#endif
+}
+template <> __device__ __forceinline__ double ld_nc<double>(const double *p)
+{
+#if SMM_GATHER_L2 == 64
+    double v; asm volatile("ld.global.nc.L2::64B.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+#elif SMM_GATHER_L2 == 128
+    double v; asm volatile("ld.global.nc.L2::128B.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+#elif SMM_GATHER_L2 == 256
+    double v; asm volatile("ld.global.nc.L2::256B.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+#else
+    return __ldg(p);
+#endif
+}
 
 // Reference-order evaluation of one destination row: links in ascending-src order, separate
 // multiply and add in float64 (pydata/sparse ndarray.COO loop; no FMA contraction).
