@@ -545,8 +545,8 @@ def _short_row_links(rng, n_src, n_dst, choices, spread=6):
 @pytest.mark.parametrize("ydt", [np.float64, np.float32])
 @pytest.mark.parametrize("n_dst", [3001, 420000])
 def test_packed_rows_parity(smm_lib, oracle, cuda, xdt, ydt, n_dst):
-    """Short-row operators run the packed-rows layout (a thread owns up to 4 rows; 256- and
-    512-thread tiles): missing values (static and per step), masks, frac, both output types."""
+    """Short-row operators run the packed-rows layout (a thread owns up to 4 rows): missing
+    values (static and per step), masks, frac, both output types, one tile and many tiles."""
     rng = np.random.default_rng(n_dst)
     n_src = n_dst * 3 // 2 + 8
     B = 37 if n_dst < 10000 else 5
@@ -564,7 +564,7 @@ def test_packed_rows_parity(smm_lib, oracle, cuda, xdt, ydt, n_dst):
     try:
         inf = _info(smm_lib, h)
         assert inf["kernel_name"] == "staged" and inf["packed_rows"] == 1, inf
-        assert inf["consumer_threads"] == (256 if n_dst < 10000 else 512), inf
+        assert inf["consumer_threads"] == 256, inf            # packed plans: two CTAs per SM
         y = _apply(smm_lib, h, x, n_dst, ydt, True, 0.5, imask, frac)
         if ydt == np.float32:
             y_ref = y_ref.astype(np.float32)
@@ -640,3 +640,27 @@ def test_nan_variation_probe(smm_lib, oracle, cuda):
             assert nan_variation_count(f, ax) == oracle.nan_variation_count_np(f, ax), (dt, ax)
     assert nan_variation_count(np.zeros((4, 1, 3), np.float32), 1) == 0           # nothing to diff
     assert nan_variation_count(np.arange(12).reshape(3, 4), 0) == 0               # integers have no NaN
+
+
+def test_more_levels_than_one_launch_holds(smm_lib, oracle, cuda):
+    """140 levels: more than the 128 a grouped launch takes, so the apply is split in two
+    balanced launches; device and host entry points."""
+    import torch
+    from smmregrid_b200 import Regridder, synth
+    L, T = 140, 3
+    w = synth.ocean3d_weights(36, 18, 24, 12, n_levels=L, seed=5)
+    n_src, n_dst = 36 * 18, 24 * 12
+    x = synth.synthetic_field((T, L, n_src), np.float32, seed=4)
+    x[:, w["src_grid_imask"] == 0] = np.nan
+    mats = oracle.compute_weights_matrix3d_np(w["src_address"], w["dst_address"], w["remap_matrix"],
+                                              w["link_length"], n_src, n_dst,
+                                              builder=oracle.compute_weights_matrix_c)
+    imask = np.stack([oracle.mask_tensordot_c(w["src_grid_imask"][l], mats[l])[0] for l in range(L)])
+    y_ref = oracle.regrid3d_np(x, 1, w.levels, w.levels, mats, imask, w["dst_grid_frac"],
+                               oracle.check_mask_np(imask), 0.5)
+    rg = Regridder(weights=w, remap_area_min=0.5)
+    n0 = smm_lib.smm_launch_count()
+    y = rg.regrid(torch.from_numpy(x).cuda()).cpu().numpy().reshape(T, L, n_dst)
+    assert smm_lib.smm_launch_count() - n0 == 2
+    assert_parity(y, y_ref, RTOL_F64, "140 levels, device")
+    assert_parity(rg.regrid(x).reshape(T, L, n_dst), y_ref, RTOL_F64, "140 levels, host")
