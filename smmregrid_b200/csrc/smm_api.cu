@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -213,15 +214,22 @@ void plan_levels(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, 
 
 // ------------------------------------------------------------------ launch dispatch
 
+constexpr int kMaxDevices = 64;
+
 template <typename TX, typename TY>
-int launch_staged_t(int lpr, int kpl, int nct, bool packed, dim3 grid, size_t smem, cudaStream_t st,
+int launch_staged_t(int dev, int lpr, int kpl, int nct, bool packed, dim3 grid, size_t smem, cudaStream_t st,
                     const JobBatch &jb, const ApplyArgs &a)
 {
 #define SMM_CASE_P(L_, K_, N_, P_)                                                                \
     if (lpr == L_ && kpl == K_ && nct == N_ && packed == P_) {                                    \
         auto kfn = staged_kernel<TX, TY, L_, K_, N_, P_>;                                         \
-        CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
-                                      static_cast<int>(smem)));                                   \
+        /* the opt-in is per kernel and device: raise it only when a launch needs more */         \
+        static std::atomic<size_t> optin[kMaxDevices];                                            \
+        if (dev < 0 || dev >= kMaxDevices || optin[dev].load(std::memory_order_relaxed) < smem) { \
+            CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                          static_cast<int>(smem)));                               \
+            if (dev >= 0 && dev < kMaxDevices) optin[dev].store(smem, std::memory_order_relaxed); \
+        }                                                                                         \
         kfn<<<grid, N_ + 32 * producer_warps(N_), smem, st>>>(jb, a);                             \
         CUDA_TRY(cudaGetLastError());                                                             \
         g_launches.fetch_add(1, std::memory_order_relaxed);                                       \
@@ -269,13 +277,22 @@ struct JobSpec {
     int32_t masked;
 };
 
-int64_t pick_chunks(int64_t B, int64_t blocks_total, int sm_count, int64_t multiple, int64_t &chunk)
+// Batch rows per work item.  A work item pays a fixed prologue (its tile's register image,
+// barriers: `prologue_us`) and the launch pays about half an item of tail per wave, so with an
+// estimated launch time T the cost is minimal near sqrt(T / (2 * prologue)) waves.  (Measured
+// on B200: the former fixed ~32-wave target cost 8-12 % at 64-512 batch rows on C2.)
+// `slots` = CTAs resident on the device, `bytes_per_row` = HBM bytes one batch row moves.
+int64_t pick_chunks(int64_t B, int64_t blocks_total, int64_t slots, double bytes_per_row, double prologue_us,
+                    int64_t multiple, int64_t &chunk)
 {
-    // ~16 waves of 2 CTAs/SM so the tail is a few percent, but at least 32 batch rows per
-    // work item so the per-item link load stays amortised.
-    const int64_t target = static_cast<int64_t>(sm_count) * 2 * 16;
-    int64_t nchunks = (target + blocks_total - 1) / std::max<int64_t>(blocks_total, 1);
-    const int64_t max_chunks = std::max<int64_t>(1, B / 32);
+    static const int k_min_rows = std::max(1, env_int("SMM_MIN_ROWS_PER_ITEM", 8));
+    static const int k_waves = env_int("SMM_WAVES", 0);                    // experiments: fixed wave count
+    const double t_us = static_cast<double>(B) * bytes_per_row / 6.5e6;     // at ~6.5 TB/s
+    double waves = k_waves > 0 ? k_waves : std::sqrt(t_us / (2.0 * prologue_us));
+    waves = std::min(32.0, std::max(1.0, waves));
+    const double items = waves * static_cast<double>(slots);
+    int64_t nchunks = static_cast<int64_t>(items / static_cast<double>(std::max<int64_t>(blocks_total, 1)) + 0.5);
+    const int64_t max_chunks = std::max<int64_t>(1, B / k_min_rows);
     nchunks = std::max<int64_t>(1, std::min(nchunks, max_chunks));
     chunk = (B + nchunks - 1) / nchunks;
     chunk = (chunk + multiple - 1) / multiple * multiple;
@@ -362,7 +379,10 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         nb_rows = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>({nb_rows, 8, B})));
         const size_t stage_bytes = row_bytes * nb_rows;
         int64_t chunk = 0;             // batch rows per work item: whole stages
-        const int64_t nchunks = pick_chunks(B, tiles_total, h->sm_count, nb_rows, chunk);
+        const double row_bytes_hbm = static_cast<double>(g1 - g0) *
+                                     (static_cast<double>(a.n_src) * sx + static_cast<double>(a.n_dst) * (y_dtype == SMM_F32 ? 4 : 8));
+        const int64_t nchunks = pick_chunks(B, tiles_total, static_cast<int64_t>(h->sm_count) * (nct == 256 ? 2 : 1),
+                                            row_bytes_hbm, nct == 256 ? 2.5 : 4.0, nb_rows, chunk);
         a.chunk = chunk; a.nchunks = static_cast<int32_t>(nchunks);
         size_t S = (nct == 256 && half > stage_off) ? (half - stage_off) / stage_bytes : 0;
         if (S < 3) S = (h->smem_optin - stage_off) / stage_bytes;        // one CTA per SM
@@ -387,7 +407,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         if (item > INT32_MAX) return fail(SMM_ERR_INVALID, "too many work items in one launch");
         if (item == 0) continue;
         const dim3 grid(static_cast<unsigned>(item));
-        const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, lpr, kpl, nct, packed, grid, smem, st, jb, a);
+        const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, h->device, lpr, kpl, nct, packed, grid, smem, st, jb, a);
         if (rc) return rc;
     }
 
@@ -408,7 +428,10 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         for (size_t g = g0; g < g1; ++g)
             blocks_total += (h->levels[gather[g].level].n_dst + rpb - 1) / rpb;
         int64_t chunk = 0;
-        const int64_t nchunks = pick_chunks(B, blocks_total, h->sm_count, kGatherBT, chunk);
+        // gather kernel: up to 8 CTAs of 256 threads per SM, a light prologue, traffic dominated by the gathers
+        const double row_bytes_hbm = static_cast<double>(nnz) * 64.0 + static_cast<double>(rows) * (y_dtype == SMM_F32 ? 4 : 8);
+        const int64_t nchunks = pick_chunks(B, blocks_total, static_cast<int64_t>(h->sm_count) * 8, row_bytes_hbm, 1.0,
+                                            kGatherBT, chunk);
         a.chunk = chunk; a.nchunks = static_cast<int32_t>(nchunks);
         a.nstages = 0; a.stage_bytes = 0; a.stage_off = 0; a.row_bytes = 0; a.rows_per_stage = 1;
         int64_t item = 0;
