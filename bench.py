@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--ydtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "staged", "gather"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "staged", "gather", "compact"])
     ap.add_argument("--nan", default="none", choices=["none", "land", "random"],
                     help="missing values in the synthetic slab: none | land (static smooth land mask, ~35%%) | random (30%% of points)")
     return ap.parse_args()
@@ -412,7 +412,9 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": avg_launch_s * 1e3,
-                     "kernel": "smm::staged_kernel" if info["kernel_name"] == "staged" else "smm::gather_kernel",
+                     "kernel": "smm::staged_kernel" if info["kernel_name"] == "staged"
+                     else ("smm::gather_kernel" if launches <= args.steps
+                           else "smm::compact_kernel + smm::compact_apply_kernel (two passes per 64 batch rows)"),
                      # stricter touched-source model: only source columns with >= 1 link
                      "achieved_touched_src": (abytes - B * (n_src - info["touched_src"]) * sx) / avg_launch_s / 1e9},
         "dst_points_per_s": world * B * n_dst * args.steps / (total_ms_max * 1e-3),

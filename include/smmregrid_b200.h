@@ -38,6 +38,10 @@ extern "C" {
 /* Which kernel family serves a level (smm_info.kernel). */
 #define SMM_KERNEL_STAGED 1 /* TMA-staged source footprint, register-resident weights     */
 #define SMM_KERNEL_GATHER 2 /* direct-gather CSR (scattered sources / oversized rows)     */
+#define SMM_KERNEL_COMPACT 3 /* smm_set_kernel only: gather-family levels take the two-pass */
+                             /* path (touched columns transposed into a compact buffer,    */
+                             /* then applied with lanes over the batch) whatever B is;     */
+                             /* by default it is chosen per apply from B and the density   */
 
 typedef struct smm_handle smm_handle;
 typedef void *smm_stream_t; /* cudaStream_t; NULL = legacy default stream */
@@ -201,7 +205,8 @@ int smm_host_plan_rowslot(const smm_host_plan *p, int32_t *rowslot);
 void smm_host_plan_free(smm_host_plan *p);
 
 /* Force a kernel family for subsequent applies (testing/benchmark aid): 0 = automatic,
- * SMM_KERNEL_STAGED (fails if the level has no staged plan) or SMM_KERNEL_GATHER. */
+ * SMM_KERNEL_STAGED (fails if the level has no staged plan), SMM_KERNEL_GATHER (direct gathers
+ * only) or SMM_KERNEL_COMPACT (two-pass path for every gather-family level). */
 int smm_set_kernel(smm_handle *h, int32_t kernel);
 
 /*

@@ -12,7 +12,7 @@ from . import _build
 
 SMM_OK, SMM_ERR_INVALID, SMM_ERR_RANGE, SMM_ERR_CUDA, SMM_ERR_ALLOC, SMM_ERR_DTYPE = range(6)
 SMM_F32, SMM_F64 = 0, 1
-SMM_KERNEL_STAGED, SMM_KERNEL_GATHER = 1, 2
+SMM_KERNEL_STAGED, SMM_KERNEL_GATHER, SMM_KERNEL_COMPACT = 1, 2, 3
 KERNEL_NAMES = {SMM_KERNEL_STAGED: "staged", SMM_KERNEL_GATHER: "gather"}
 
 i32, i64, f64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_double

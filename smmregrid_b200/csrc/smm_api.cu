@@ -54,6 +54,8 @@ struct LevelDev {
     uint16_t *iplan = nullptr;
     int32_t *rowmap = nullptr;          // tile slot -> row (re-ordered plans) | packed plans: the rowslot table
     bool packed = false, reordered = false;
+    int32_t *tcols = nullptr, *blk_ptr = nullptr, *rcol = nullptr;   // compact (two-pass) plan of gather levels
+    int32_t compact_blocks = 0;
     int32_t *imask = nullptr;
     double *frac = nullptr;
     bool has_imask = false, has_frac = false;
@@ -77,6 +79,10 @@ struct smm_handle {
     int force_kernel = 0;
     double renorm_min_valid = -1.0;      // opt-in extension, see smm_set_renormalize
     std::vector<LevelDev> levels;
+    // stream-ordered pool for the compact path's transposed buffer; keeps its memory between
+    // applies (re-mapping ~1 GB per call cost 8 ms against 1.9 ms of kernels), freed with the handle
+    mutable std::mutex pool_mu;
+    mutable cudaMemPool_t pool = nullptr;
     std::mutex host_mu;
     HostSlot slots[3];
 };
@@ -99,6 +105,7 @@ void free_level(LevelDev &L)
     cudaFree(L.rowptr); cudaFree(L.col); cudaFree(L.val);
     cudaFree(L.tiles); cudaFree(L.segs); cudaFree(L.wplan); cudaFree(L.iplan); cudaFree(L.rowmap);
     cudaFree(L.imask); cudaFree(L.frac);
+    cudaFree(L.tcols); cudaFree(L.blk_ptr); cudaFree(L.rcol);
     L = LevelDev{};
 }
 
@@ -126,6 +133,15 @@ int upload_level(const HostCsr &csr, const HostPlan &plan, LevelDev &L)
         L.reordered = plan.reordered;
         if (plan.packed) { if ((rc = upload(&L.rowmap, plan.rowslot, L.device_bytes))) return rc; }
         else if (!plan.rowmap.empty() && (rc = upload(&L.rowmap, plan.rowmap, L.device_bytes))) return rc;
+    }
+    if (!plan.ok && L.nnz > 0) {
+        // scattered sources: the two-pass compact path needs the touched columns and link ranks
+        CompactPlan cp;
+        build_compact(csr, kCompactW, cp);
+        L.compact_blocks = static_cast<int32_t>(cp.blk_ptr.size()) - 1;
+        if ((rc = upload(&L.tcols, cp.tcols, L.device_bytes))) return rc;
+        if ((rc = upload(&L.blk_ptr, cp.blk_ptr, L.device_bytes))) return rc;
+        if ((rc = upload(&L.rcol, cp.rcol, L.device_bytes))) return rc;
     }
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&L.imask), static_cast<size_t>(L.n_dst) * sizeof(int32_t)));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&L.frac), static_cast<size_t>(L.n_dst) * sizeof(double)));
@@ -299,6 +315,60 @@ int64_t pick_chunks(int64_t B, int64_t blocks_total, int64_t slots, double bytes
     return (B + chunk - 1) / chunk;
 }
 
+// Two-pass apply of one gather-family level (see compact_kernel): per chunk of <= 64 batch rows,
+// transpose the touched source columns into XT, then apply the links from XT.  XT comes from the
+// stream-ordered allocator, so concurrent applies on other streams stay independent.
+template <typename TX, typename TY>
+int launch_compact_t(const smm_handle *h, const LevelDev &L, const JobSpec &sp, int64_t B, int64_t xbs,
+                     int64_t ybs, double area_min, cudaStream_t st)
+{
+    {
+        std::lock_guard<std::mutex> lock(h->pool_mu);
+        if (!h->pool) {
+            cudaMemPoolProps props{};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = h->device;
+            CUDA_TRY(cudaMemPoolCreate(&h->pool, &props));
+            uint64_t keep = UINT64_MAX;
+            CUDA_TRY(cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+    }
+    TX *xt = nullptr;
+    const size_t xt_bytes = std::max<size_t>(static_cast<size_t>(L.touched), 1) * kCompactBC * sizeof(TX);
+    CUDA_TRY(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&xt), xt_bytes, h->pool, st));
+    const size_t smem = static_cast<size_t>(kCompactBC) * (kCompactW + 1) * sizeof(TX);
+    static std::atomic<bool> optin[kMaxDevices];
+    if (h->device >= kMaxDevices || !optin[h->device].load(std::memory_order_relaxed)) {
+        cudaError_t e = cudaFuncSetAttribute(compact_kernel<TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem));
+        if (e != cudaSuccess) { cudaFreeAsync(xt, st); return fail(SMM_ERR_CUDA, cudaGetErrorString(e)); }
+        if (h->device < kMaxDevices) optin[h->device].store(true, std::memory_order_relaxed);
+    }
+    const unsigned grid2 = static_cast<unsigned>((L.n_dst + kCompactRows - 1) / kCompactRows);
+    cudaError_t e = cudaSuccess;
+    for (int64_t b0 = 0; b0 < B && e == cudaSuccess; b0 += kCompactBC) {
+        const int bc = static_cast<int>(std::min<int64_t>(kCompactBC, B - b0));
+        compact_kernel<TX><<<static_cast<unsigned>(L.compact_blocks), kCompactThreads,
+                             static_cast<size_t>(bc) * (kCompactW + 1) * sizeof(TX), st>>>(
+            static_cast<const TX *>(sp.x) + b0 * xbs, xbs, L.n_src, bc, L.tcols, L.blk_ptr, xt);
+        compact_apply_kernel<TX, TY><<<grid2, kCompactThreads, 0, st>>>(
+            xt, bc, L.rowptr, L.rcol, L.val, L.imask, L.frac, sp.masked, area_min, L.n_dst,
+            static_cast<TY *>(sp.y) + b0 * ybs, ybs);
+        e = cudaGetLastError();
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+    }
+    cudaFreeAsync(xt, st);
+    if (e != cudaSuccess) return fail(SMM_ERR_CUDA, std::string("compact apply: ") + cudaGetErrorString(e));
+    return SMM_OK;
+}
+
+int launch_compact(const smm_handle *h, const LevelDev &L, const JobSpec &sp, int32_t x_dtype, int32_t y_dtype,
+                   int64_t B, int64_t xbs, int64_t ybs, double area_min, cudaStream_t st)
+{
+    return SMM_DTYPE_DISPATCH(launch_compact_t, h, L, sp, B, xbs, ybs, area_min, st);
+}
+
 int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t x_dtype,
                 int32_t y_dtype, int64_t B, int64_t xbs, int64_t ybs, double area_min,
                 cudaStream_t st)
@@ -409,6 +479,27 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         const dim3 grid(static_cast<unsigned>(item));
         const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, h->device, lpr, kpl, nct, packed, grid, smem, st, jb, a);
         if (rc) return rc;
+    }
+
+    // ---- compact (two-pass) launches: scattered sources with enough batch rows, one level at a time
+    {
+        std::vector<JobSpec> plain;
+        for (const JobSpec &sp : gather) {
+            const LevelDev &L = h->levels[sp.level];
+            // Cost per batch row in HBM-byte equivalents, calibrated on B200 (C5nn / C5dis, f32 and
+            // f64): a random gather costs ~120 bytes (a 64-byte sector at about half the streaming
+            // rate); the two passes move the slab, the touched columns twice-ish and the links, at
+            // ~2/3 of the streaming rate.  Runs of fewer than 16 batch values are not worth it.
+            const double gather_cost = static_cast<double>(L.nnz) * 120.0;
+            const double compact_cost = 1.5 * (static_cast<double>(L.n_src) + static_cast<double>(L.touched) +
+                                               static_cast<double>(L.nnz)) * static_cast<double>(sx);
+            bool use = L.rcol && h->renorm_min_valid < 0.0 && h->force_kernel != SMM_KERNEL_GATHER;
+            if (h->force_kernel != SMM_KERNEL_COMPACT) use = use && B >= 16 && gather_cost > compact_cost;
+            if (!use) { plain.push_back(sp); continue; }
+            const int rc = launch_compact(h, L, sp, x_dtype, y_dtype, B, xbs, ybs, area_min, st);
+            if (rc) return rc;
+        }
+        gather.swap(plain);
     }
 
     // ---- gather launches
@@ -673,6 +764,7 @@ int smm_destroy(smm_handle *h)
     {
         DeviceGuard g(h->device);
         for (LevelDev &L : h->levels) free_level(L);
+        if (h->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(h->pool); }
         for (HostSlot &s : h->slots) {
             cudaFree(s.dx); cudaFree(s.dy);
             cudaFreeHost(s.px); cudaFreeHost(s.py);
@@ -986,8 +1078,8 @@ void smm_host_plan_free(smm_host_plan *p) { delete p; }
 int smm_set_kernel(smm_handle *h, int32_t kernel)
 {
     if (!h) return fail(SMM_ERR_INVALID, "null handle");
-    if (kernel != 0 && kernel != SMM_KERNEL_STAGED && kernel != SMM_KERNEL_GATHER)
-        return fail(SMM_ERR_INVALID, "kernel must be 0, SMM_KERNEL_STAGED or SMM_KERNEL_GATHER");
+    if (kernel != 0 && kernel != SMM_KERNEL_STAGED && kernel != SMM_KERNEL_GATHER && kernel != SMM_KERNEL_COMPACT)
+        return fail(SMM_ERR_INVALID, "kernel must be 0, SMM_KERNEL_STAGED, SMM_KERNEL_GATHER or SMM_KERNEL_COMPACT");
     h->force_kernel = kernel;
     return SMM_OK;
 }

@@ -633,6 +633,99 @@ gather_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
     }
 }
 
+// ------------------------------------------------------------------ compact (two-pass) path
+//
+// Scattered sources (unstructured grids in file order): a direct gather pulls a 64-byte sector
+// per 4-byte element.  With enough batch rows it is cheaper to (1) read the slab once, fully
+// coalesced, and write the TOUCHED source columns transposed into a compact buffer
+// XT[n_touched][BC] (BC = batch rows of the chunk, <= 64: every column becomes one contiguous
+// run), then (2) apply the links from XT, where a link is one coalesced run of BC values, with
+// lanes over the batch.  Pass 2 sums each (row, batch row) in the reference's own order
+// (ascending source, separate multiply and add), so the results are bit-identical to a
+// reference-order evaluation and no threshold replay is needed.
+
+constexpr int kCompactBC = 64;          // batch rows per chunk (lanes handle b and b + 32)
+constexpr int kCompactW = 256;          // source columns per pass-1 block
+constexpr int kCompactThreads = 256;
+constexpr int kCompactRows = 32;        // destination rows per pass-2 block
+
+// Pass 1.  Block i owns source columns [i*W, (i+1)*W) and the touched columns among them,
+// tcols[blk_ptr[i] .. blk_ptr[i+1]) (ascending; their rank in tcols is the row of XT).
+template <typename TX>
+__global__ void __launch_bounds__(kCompactThreads)
+compact_kernel(const TX *__restrict__ x, int64_t x_bstride, int64_t n_src, int bc,
+               const int32_t *__restrict__ tcols, const int32_t *__restrict__ blk_ptr, TX *__restrict__ xt)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TX *tile = reinterpret_cast<TX *>(smem_raw);                 // [bc][W + 1]
+    const int t0 = blk_ptr[blockIdx.x], t1 = blk_ptr[blockIdx.x + 1];
+    if (t0 == t1) return;                                        // nothing touched here: not read at all
+    const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kCompactW;
+    const int w = static_cast<int>((n_src - c0 < kCompactW) ? n_src - c0 : kCompactW);
+    const int tid = threadIdx.x;
+    if (tid < w) {
+        // asynchronous element copies straight into shared memory (LDGSTS): all bc rows of this
+        // thread's column are in flight at once, at no register cost
+        const TX *xc = x + c0 + tid;
+        const uint32_t dst0 = smem_u32(tile + tid);
+#pragma unroll 8
+        for (int b = 0; b < bc; ++b)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst0 + static_cast<uint32_t>(b * (kCompactW + 1) * sizeof(TX))),
+                         "l"(xc + b * x_bstride), "n"(sizeof(TX))
+                         : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int t = t0 + warp; t < t1; t += kCompactThreads / 32) {
+        const int c = tcols[t] - static_cast<int>(c0);
+        TX *dst = xt + static_cast<int64_t>(t) * kCompactBC;
+        if (lane < bc) dst[lane] = tile[lane * (kCompactW + 1) + c];
+        if (lane + 32 < bc) dst[lane + 32] = tile[(lane + 32) * (kCompactW + 1) + c];
+    }
+}
+
+// Pass 2.  Block = 32 destination rows x bc batch rows; warp w takes rows w, w + 8, ...; lanes are
+// batch rows.  rcol[j] = rank of link j's source column in tcols.
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(kCompactThreads)
+compact_apply_kernel(const TX *__restrict__ xt, int bc, const int32_t *__restrict__ rowptr,
+                     const int32_t *__restrict__ rcol, const double *__restrict__ val,
+                     const int32_t *__restrict__ imask, const double *__restrict__ frac, int masked,
+                     double remap_area_min, int64_t n_dst, TY *__restrict__ y, int64_t y_bstride)
+{
+    __shared__ TY out[kCompactBC][kCompactRows + 1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kCompactRows;
+    for (int rl = warp; rl < kCompactRows; rl += kCompactThreads / 32) {
+        const int64_t row = row0 + rl;
+        if (row >= n_dst) break;
+        bool dead = false;
+        if (masked && imask[row] == 0) dead = true;
+        if (remap_area_min > 0.0 && frac[row] < remap_area_min) dead = true;
+        double a0 = 0.0, a1 = 0.0;
+        const int j1 = rowptr[row + 1];
+#pragma unroll 4
+        for (int j = rowptr[row]; j < j1; ++j) {
+            const TX *src = xt + static_cast<int64_t>(__ldg(rcol + j)) * kCompactBC;
+            const double wj = __ldg(val + j);
+            const TX v0 = lane < bc ? fill_invalid(__ldg(src + lane)) : TX(0);
+            const TX v1 = lane + 32 < bc ? fill_invalid(__ldg(src + lane + 32)) : TX(0);
+            a0 = __dadd_rn(a0, __dmul_rn(static_cast<double>(v0), wj));      // reference order, no FMA
+            a1 = __dadd_rn(a1, __dmul_rn(static_cast<double>(v1), wj));
+        }
+        if (a0 > 1e19) a0 = CUDART_NAN;                                       // regrid.py:570
+        if (a1 > 1e19) a1 = CUDART_NAN;
+        out[lane][rl] = static_cast<TY>(dead ? CUDART_NAN : a0);
+        out[lane + 32][rl] = static_cast<TY>(dead ? CUDART_NAN : a1);
+    }
+    __syncthreads();
+    const int nrows = static_cast<int>((n_dst - row0 < kCompactRows) ? n_dst - row0 : kCompactRows);
+    for (int b = warp; b < bc; b += kCompactThreads / 32)
+        if (lane < nrows) y[b * y_bstride + row0 + lane] = out[b][lane];
+}
+
 // ------------------------------------------------------------------ mask_tensordot
 
 // weights.py:47-52.  One thread per destination row, links in ascending-src order, separate

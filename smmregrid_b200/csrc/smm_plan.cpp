@@ -646,4 +646,22 @@ void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_
     if (alt.ok && (!plan.ok || plan_cost(alt) < 0.8 * plan_cost(plan))) plan = std::move(alt);
 }
 
+void build_compact(const HostCsr &csr, int32_t block_cols, CompactPlan &out)
+{
+    out = CompactPlan{};
+    std::vector<int32_t> rank(static_cast<size_t>(csr.n_src), -1);
+    for (int32_t c : csr.col) rank[c] = 0;
+    const int64_t nblk = (csr.n_src + block_cols - 1) / block_cols;
+    out.blk_ptr.assign(static_cast<size_t>(nblk) + 1, 0);
+    for (int64_t c = 0; c < csr.n_src; ++c) {
+        if (rank[c] < 0) continue;
+        rank[c] = static_cast<int32_t>(out.tcols.size());
+        out.tcols.push_back(static_cast<int32_t>(c));
+        ++out.blk_ptr[c / block_cols + 1];
+    }
+    for (int64_t i = 0; i < nblk; ++i) out.blk_ptr[i + 1] += out.blk_ptr[i];
+    out.rcol.resize(csr.col.size());
+    for (size_t j = 0; j < csr.col.size(); ++j) out.rcol[j] = rank[csr.col[j]];
+}
+
 }  // namespace smm

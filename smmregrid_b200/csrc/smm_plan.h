@@ -19,6 +19,16 @@ struct HostCsr {
     int64_t touched_src = 0;
 };
 
+// Compact (two-pass) plan of a level served by the gather family: the touched source columns in
+// ascending order, their range per block of `block_cols` source columns, and every link's
+// column replaced by its rank among the touched columns (see compact_kernel).
+struct CompactPlan {
+    std::vector<int32_t> tcols;      // [touched_src]
+    std::vector<int32_t> blk_ptr;    // [ceil(n_src / block_cols) + 1]
+    std::vector<int32_t> rcol;       // [nnz]
+};
+void build_compact(const HostCsr &csr, int32_t block_cols, CompactPlan &out);
+
 // Returns 0 on success, SMM_ERR_* otherwise (message in err).
 int build_csr(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t *src_address,
               const int32_t *dst_address, const double *remap_matrix, int32_t num_wgts,

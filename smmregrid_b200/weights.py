@@ -198,7 +198,8 @@ class WeightsMatrix:
         _lib.check(_lib.load().smm_set_renormalize(self.handle, v))
 
     def set_kernel(self, kernel: Optional[str]):
-        code = {None: 0, "auto": 0, "staged": _lib.SMM_KERNEL_STAGED, "gather": _lib.SMM_KERNEL_GATHER}[kernel]
+        code = {None: 0, "auto": 0, "staged": _lib.SMM_KERNEL_STAGED, "gather": _lib.SMM_KERNEL_GATHER,
+                "compact": _lib.SMM_KERNEL_COMPACT}[kernel]
         _lib.check(_lib.load().smm_set_kernel(self.handle, code))
 
 

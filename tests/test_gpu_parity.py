@@ -664,3 +664,65 @@ def test_more_levels_than_one_launch_holds(smm_lib, oracle, cuda):
     assert smm_lib.smm_launch_count() - n0 == 2
     assert_parity(y, y_ref, RTOL_F64, "140 levels, device")
     assert_parity(rg.regrid(x).reshape(T, L, n_dst), y_ref, RTOL_F64, "140 levels, host")
+
+
+@pytest.mark.parametrize("xdt", [np.float32, np.float64])
+@pytest.mark.parametrize("ydt", [np.float64, np.float32])
+@pytest.mark.parametrize("B", [1, 37, 64, 130])
+def test_compact_two_pass_path(smm_lib, oracle, cuda, xdt, ydt, B):
+    """Scattered sources: the two-pass path (touched columns transposed into a compact buffer,
+    links applied with lanes over the batch) sums in the reference's own order, so float64
+    results are BIT-IDENTICAL to the reference-order oracle."""
+    rng = np.random.default_rng(1000 + B)
+    n_src, n_dst = 400001, 3001                   # odd sizes: partial column block, partial row block
+    src, dst, w = random_links(rng, n_src, n_dst, 3, dup_frac=0.05, sort=False, negative=True)
+    x = (280 + 20 * rng.standard_normal((B, n_src))).astype(xdt)
+    x[rng.random(x.shape) < 0.03] = np.nan
+    x[0, src[0] - 1] = np.inf
+    imask = (rng.random(n_dst) > 0.1).astype(np.int32)
+    frac = rng.random(n_dst)
+    mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, imask, frac, 0.5, True)
+    h = _create(smm_lib, src, dst, w, n_src, n_dst)
+    try:
+        assert _info(smm_lib, h)["kernel_name"] == "gather"
+        n0 = smm_lib.smm_launch_count()
+        y = _apply(smm_lib, h, x, n_dst, ydt, True, 0.5, imask, frac, kernel=3)
+        assert smm_lib.smm_launch_count() - n0 == 2 * ((B + 63) // 64)          # two passes per 64 batch rows
+        if ydt == np.float64:
+            assert_parity(y, y_ref, RTOL_F64, "compact f64 out")
+            diff = ~((y == y_ref) | (np.isnan(y) & np.isnan(y_ref)))
+            assert not diff.any(), (int(diff.sum()), y[diff][:4], y_ref[diff][:4])
+        else:
+            assert_parity(y, y_ref.astype(np.float32), RTOL_F32, "compact f32 out")
+        # automatic choice (direct gathers here: few links per source column).  The weights of this
+        # case change sign, so sums cancel and an order-changing kernel is only accurate relative
+        # to the magnitude of the terms, not of the result: looser relative tolerance
+        y_auto = _apply(smm_lib, h, x, n_dst, ydt, True, 0.5, imask, frac, kernel=0)
+        assert_parity(y_auto, y_ref.astype(ydt), 1e-9 if ydt == np.float64 else 1e-5, "auto")
+    finally:
+        smm_lib.smm_destroy(h)
+
+
+def test_compact_path_is_chosen_for_dense_scattered_operators(smm_lib, oracle, cuda):
+    """C5dis-like (4 links per row, random source order): with >= 16 batch rows the apply takes
+    the two-pass path by itself; a sparse nn-like operator keeps the direct gathers."""
+    from smmregrid_b200 import synth
+    for cfg, expect_compact in (("C5dis", True), ("C5nn", False)):
+        w = synth.config_weights(cfg, 8)
+        n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+        x = synth.synthetic_field((40, n_src), np.float32, seed=3, nan_mode="random")
+        mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+        y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False, nthreads=4)
+        h = _create(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+        try:
+            n0 = smm_lib.smm_launch_count()
+            y = _apply(smm_lib, h, x, n_dst, np.float64, False, 0.0)
+            assert (smm_lib.smm_launch_count() - n0 == 2) == expect_compact, cfg
+            assert_parity(y, y_ref, RTOL_F64, cfg)
+            n0 = smm_lib.smm_launch_count()
+            y8 = _apply(smm_lib, h, np.ascontiguousarray(x[:8]), n_dst, np.float64, False, 0.0)   # few rows: direct gathers
+            assert smm_lib.smm_launch_count() - n0 == 1
+            assert_parity(y8, y_ref[:8], RTOL_F64, cfg + " B=8")
+        finally:
+            smm_lib.smm_destroy(h)
