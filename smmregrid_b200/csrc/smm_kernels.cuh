@@ -644,8 +644,14 @@ gather_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
 // (ascending source, separate multiply and add), so the results are bit-identical to a
 // reference-order evaluation and no threshold replay is needed.
 
-constexpr int kCompactBC = 64;          // batch rows per chunk (lanes handle b and b + 32)
-constexpr int kCompactW = 256;          // source columns per pass-1 block
+#ifndef SMM_COMPACT_BC
+#define SMM_COMPACT_BC 64
+#endif
+#ifndef SMM_COMPACT_W
+#define SMM_COMPACT_W 256
+#endif
+constexpr int kCompactBC = SMM_COMPACT_BC;   // batch rows per chunk (lanes handle b and b + 32)
+constexpr int kCompactW = SMM_COMPACT_W;     // source columns per pass-1 block
 constexpr int kCompactThreads = 256;
 constexpr int kCompactRows = 32;        // destination rows per pass-2 block
 
@@ -663,11 +669,11 @@ compact_kernel(const TX *__restrict__ x, int64_t x_bstride, int64_t n_src, int b
     const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kCompactW;
     const int w = static_cast<int>((n_src - c0 < kCompactW) ? n_src - c0 : kCompactW);
     const int tid = threadIdx.x;
-    if (tid < w) {
+    for (int col = tid; col < w; col += kCompactThreads) {
         // asynchronous element copies straight into shared memory (LDGSTS): all bc rows of this
         // thread's column are in flight at once, at no register cost
-        const TX *xc = x + c0 + tid;
-        const uint32_t dst0 = smem_u32(tile + tid);
+        const TX *xc = x + c0 + col;
+        const uint32_t dst0 = smem_u32(tile + col);
 #pragma unroll 8
         for (int b = 0; b < bc; ++b)
             asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst0 + static_cast<uint32_t>(b * (kCompactW + 1) * sizeof(TX))),
@@ -682,7 +688,7 @@ compact_kernel(const TX *__restrict__ x, int64_t x_bstride, int64_t n_src, int b
         const int c = tcols[t] - static_cast<int>(c0);
         TX *dst = xt + static_cast<int64_t>(t) * kCompactBC;
         if (lane < bc) dst[lane] = tile[lane * (kCompactW + 1) + c];
-        if (lane + 32 < bc) dst[lane + 32] = tile[(lane + 32) * (kCompactW + 1) + c];
+        if (kCompactBC > 32 && lane + 32 < bc) dst[lane + 32] = tile[(lane + 32) * (kCompactW + 1) + c];
     }
 }
 
@@ -718,7 +724,7 @@ compact_apply_kernel(const TX *__restrict__ xt, int bc, const int32_t *__restric
         if (a0 > 1e19) a0 = CUDART_NAN;                                       // regrid.py:570
         if (a1 > 1e19) a1 = CUDART_NAN;
         out[lane][rl] = static_cast<TY>(dead ? CUDART_NAN : a0);
-        out[lane + 32][rl] = static_cast<TY>(dead ? CUDART_NAN : a1);
+        if (kCompactBC > 32) out[(lane + 32) % kCompactBC][rl] = static_cast<TY>(dead ? CUDART_NAN : a1);
     }
     __syncthreads();
     const int nrows = static_cast<int>((n_dst - row0 < kCompactRows) ? n_dst - row0 : kCompactRows);
