@@ -1,5 +1,5 @@
 """Property tests on the GPU (hypothesis): random link sets, NaN/inf patterns, masks, dtypes and
-strides against the oracle -- both kernel families, every lane configuration."""
+strides against the oracle -- all kernel families, every lane configuration."""
 import ctypes
 import os
 
@@ -66,7 +66,7 @@ def test_random_operator_matches_oracle(smm_lib, oracle, cuda, c):
         tol = 1e-12 if c["ydt"] == np.float64 else 1e-6
         with np.errstate(over="ignore"):
             ref = y_ref.astype(c["ydt"])
-        for kernel in (0, 2):
+        for kernel in (0, 2, 3):           # automatic, direct gathers, two-pass compact path for gather-family levels
             _lib.check(smm_lib.smm_set_kernel(h, kernel))
             y = torch.full((B, n_dst), 3.0, dtype=torch.float64 if c["ydt"] == np.float64 else torch.float32, device="cuda")
             _lib.check(smm_lib.smm_apply(h, 0, xd.data_ptr(), 0 if c["x"].dtype == np.float32 else 1, B, ldx,
