@@ -527,9 +527,18 @@ def test_levels_mixed_kernels_and_empty_level(smm_lib, oracle, cuda):
     for T in (1, 7):
         x = synth.synthetic_field((T, 4, n_src), np.float32, seed=T, nan_mode="random")
         y_ref = oracle.regrid3d_np(x, 1, w.levels, w.levels, mats, imask, v["dst_grid_frac"], masked, 0.0)
-        y = rg.regrid(x).reshape(T, 4, n_dst)
-        assert_parity(y, y_ref, RTOL_F64, f"mixed T={T}")
-        assert np.isnan(y[:, 2]).all()                     # no links -> masked level -> NaN everywhere
+        for kernel in (None, "compact"):                   # compact: the scattered level takes the two-pass path
+            rg.weights_matrix.set_kernel(kernel)
+            y = rg.regrid(x).reshape(T, 4, n_dst)
+            assert_parity(y, y_ref, RTOL_F64, f"mixed T={T} {kernel}")
+            assert np.isnan(y[:, 2]).all()                 # no links -> masked level -> NaN everywhere
+    # many time steps, device data with the level stride (the scattered level may go two-pass by itself)
+    import torch
+    rg.weights_matrix.set_kernel(None)
+    x = synth.synthetic_field((40, 4, n_src), np.float32, seed=9, nan_mode="random")
+    y_ref = oracle.regrid3d_np(x, 1, w.levels, w.levels, mats, imask, v["dst_grid_frac"], masked, 0.0)
+    y = rg.regrid(torch.from_numpy(x).cuda()).cpu().numpy().reshape(40, 4, n_dst)
+    assert_parity(y, y_ref, RTOL_F64, "mixed T=40")
 
 
 def _short_row_links(rng, n_src, n_dst, choices, spread=6):
