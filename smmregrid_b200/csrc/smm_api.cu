@@ -405,7 +405,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
     a.B = B; a.x_bstride = xbs; a.y_bstride = ybs; a.remap_area_min = area_min;
     a.renorm_min_valid = h->renorm_min_valid;
     // experiment switches are read once per process, not per launch
-    static const uint32_t k_debug_flags = env_int("SMM_DEBUG_STREAM_ONLY", 0) == 1 ? 1u : 0u;
+    static const uint32_t k_debug_flags = static_cast<uint32_t>(env_int("SMM_DEBUG_STREAM_ONLY", 0)) & 3u;
     static const int k_max_stages = std::max(2, env_int("SMM_MAX_STAGES", kMaxStages));
     a.debug_flags = k_debug_flags;   // bit 0: staged consumers skip the arithmetic (profiling aid)
 
