@@ -202,6 +202,12 @@ int smm_host_plan_rowmap(const smm_host_plan *p, int32_t *rowmap);
  * starts in sub-row u (link slots 4u..4u+3) of thread t at [tile][u][t]; -1 none, -2 the sub-row
  * continues the row of sub-row u-1. */
 int smm_host_plan_rowslot(const smm_host_plan *p, int32_t *rowslot);
+/* Two-pass compact plan of the operator (what gather-family levels upload for the compact path):
+ * tcols [touched_src] = touched source columns, ascending; blk_ptr [n_blocks + 1] = their range
+ * per block of 256 source columns; rcol [nnz] = rank in tcols of every CSR link's column.  Call
+ * once with NULL arrays for the sizes. */
+int smm_host_plan_compact(const smm_host_plan *p, int64_t *n_touched_out, int64_t *n_blocks_out,
+                          int32_t *tcols, int32_t *blk_ptr, int32_t *rcol);
 void smm_host_plan_free(smm_host_plan *p);
 
 /* Force a kernel family for subsequent applies (testing/benchmark aid): 0 = automatic,

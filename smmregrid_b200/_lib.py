@@ -53,6 +53,7 @@ SIGNATURES = {
     "smm_host_plan_copy": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "smm_host_plan_rowmap": (ctypes.c_int, [vp, vp]),
     "smm_host_plan_rowslot": (ctypes.c_int, [vp, vp]),
+    "smm_host_plan_compact": (ctypes.c_int, [vp, P(i64), P(i64), vp, vp, vp]),
     "smm_host_plan_free": (None, [vp]),
     "smm_set_kernel": (ctypes.c_int, [vp, i32]),
     "smm_set_renormalize": (ctypes.c_int, [vp, f64]),

@@ -1073,6 +1073,19 @@ int smm_host_plan_rowslot(const smm_host_plan *p, int32_t *rowslot)
     return SMM_OK;
 }
 
+int smm_host_plan_compact(const smm_host_plan *p, int64_t *n_touched_out, int64_t *n_blocks_out,
+                          int32_t *tcols, int32_t *blk_ptr, int32_t *rcol)
+{
+    if (!p) return fail(SMM_ERR_INVALID, "null plan");
+    CompactPlan cp;
+    build_compact(p->csr, kCompactW, cp);
+    if (n_touched_out) *n_touched_out = static_cast<int64_t>(cp.tcols.size());
+    if (n_blocks_out) *n_blocks_out = static_cast<int64_t>(cp.blk_ptr.size()) - 1;
+    auto cpv = [](int32_t *dst, const std::vector<int32_t> &v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(int32_t)); };
+    cpv(tcols, cp.tcols); cpv(blk_ptr, cp.blk_ptr); cpv(rcol, cp.rcol);
+    return SMM_OK;
+}
+
 void smm_host_plan_free(smm_host_plan *p) { delete p; }
 
 int smm_set_kernel(smm_handle *h, int32_t kernel)

@@ -264,3 +264,35 @@ def test_packed_rows_fall_back_when_footprint_too_large(smm_lib, oracle):
     mat = oracle.compute_weights_matrix_c(src + 1, dst + 1, w, n_src, n_dst)
     x = rng.standard_normal((2, n_src))
     assert_parity(p.emulate(x), oracle.apply_weights_c(x, mat, None, None, 0.0, False), 1e-12)
+
+
+def test_compact_plan_of_scattered_operator(smm_lib):
+    """Two-pass compact plan (uploaded for gather-family levels): touched columns ascending, block
+    ranges over 256-column blocks, link columns replaced by their rank."""
+    from smmregrid_b200 import _lib
+    rng = np.random.default_rng(4)
+    n_src, n_dst = 100_003, 700
+    src, dst, w = random_links(rng, n_src, n_dst, 3, dup_frac=0.1, sort=False)
+    s32, d32 = np.ascontiguousarray(src, np.int32), np.ascontiguousarray(dst, np.int32)
+    h = ctypes.c_void_p()
+    _lib.check(smm_lib.smm_host_plan_build(n_src, n_dst, s32.size, s32.ctypes.data, d32.ctypes.data,
+                                           w.ctypes.data, 1, 1, ctypes.byref(h)))
+    try:
+        inf = _lib.SmmInfo()
+        _lib.check(smm_lib.smm_host_plan_info(h, ctypes.byref(inf), None))
+        rowptr = np.empty(n_dst + 1, np.int32); col = np.empty(inf.nnz, np.int32); val = np.empty(inf.nnz)
+        _lib.check(smm_lib.smm_host_plan_copy(h, rowptr.ctypes.data, col.ctypes.data, val.ctypes.data, None, None, None, None))
+        nt, nb = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(smm_lib.smm_host_plan_compact(h, ctypes.byref(nt), ctypes.byref(nb), None, None, None))
+        assert nt.value == inf.touched_src == np.unique(col).size and nb.value == -(-n_src // 256)
+        tcols = np.empty(nt.value, np.int32); blk = np.empty(nb.value + 1, np.int32); rcol = np.empty(inf.nnz, np.int32)
+        _lib.check(smm_lib.smm_host_plan_compact(h, None, None, tcols.ctypes.data, blk.ctypes.data, rcol.ctypes.data))
+        assert np.array_equal(tcols, np.unique(col))
+        assert np.array_equal(tcols[rcol], col)                                  # rank -> column round trip
+        assert blk[0] == 0 and blk[-1] == nt.value and (np.diff(blk) >= 0).all()
+        for i in (0, 7, nb.value - 1):                                           # block i holds columns [256 i, 256 (i + 1))
+            c = tcols[blk[i]:blk[i + 1]]
+            assert ((c >= 256 * i) & (c < 256 * (i + 1))).all()
+            assert c.size == ((np.unique(col) // 256) == i).sum()
+    finally:
+        smm_lib.smm_host_plan_free(h)
