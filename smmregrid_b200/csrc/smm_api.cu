@@ -315,6 +315,8 @@ int64_t pick_chunks(int64_t B, int64_t blocks_total, int64_t slots, double bytes
     return (B + chunk - 1) / chunk;
 }
 
+constexpr int kCompactUnavailable = -1;   // launch_compact: nothing was launched, use the gather kernel
+
 // Two-pass apply of one gather-family level (see compact_kernel): per chunk of <= 64 batch rows,
 // transpose the touched source columns into XT, then apply the links from XT.  XT comes from the
 // stream-ordered allocator, so concurrent applies on other streams stay independent.
@@ -329,14 +331,21 @@ int launch_compact_t(const smm_handle *h, const LevelDev &L, const JobSpec &sp, 
             props.allocType = cudaMemAllocationTypePinned;
             props.location.type = cudaMemLocationTypeDevice;
             props.location.id = h->device;
-            CUDA_TRY(cudaMemPoolCreate(&h->pool, &props));
             uint64_t keep = UINT64_MAX;
-            CUDA_TRY(cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            if (cudaMemPoolCreate(&h->pool, &props) != cudaSuccess ||
+                cudaMemPoolSetAttribute(h->pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) {
+                cudaGetLastError();
+                if (h->pool) { cudaMemPoolDestroy(h->pool); h->pool = nullptr; }
+                return kCompactUnavailable;          // no stream-ordered pools here: direct gathers instead
+            }
         }
     }
     TX *xt = nullptr;
     const size_t xt_bytes = std::max<size_t>(static_cast<size_t>(L.touched), 1) * kCompactBC * sizeof(TX);
-    CUDA_TRY(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&xt), xt_bytes, h->pool, st));
+    if (cudaMallocFromPoolAsync(reinterpret_cast<void **>(&xt), xt_bytes, h->pool, st) != cudaSuccess) {
+        cudaGetLastError();
+        return kCompactUnavailable;                  // not enough memory for the transposed buffer
+    }
     const size_t smem = static_cast<size_t>(kCompactBC) * (kCompactW + 1) * sizeof(TX);
     static std::atomic<bool> optin[kMaxDevices];
     if (h->device >= kMaxDevices || !optin[h->device].load(std::memory_order_relaxed)) {
@@ -497,6 +506,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
             if (h->force_kernel != SMM_KERNEL_COMPACT) use = use && B >= 16 && gather_cost > compact_cost;
             if (!use) { plain.push_back(sp); continue; }
             const int rc = launch_compact(h, L, sp, x_dtype, y_dtype, B, xbs, ybs, area_min, st);
+            if (rc == kCompactUnavailable) { plain.push_back(sp); continue; }
             if (rc) return rc;
         }
         gather.swap(plain);
