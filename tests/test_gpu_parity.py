@@ -735,3 +735,44 @@ def test_compact_path_is_chosen_for_dense_scattered_operators(smm_lib, oracle, c
             assert_parity(y8, y_ref[:8], RTOL_F64, cfg + " B=8")
         finally:
             smm_lib.smm_destroy(h)
+
+
+def test_c5_full_size_properties(smm_lib, cuda):
+    """C5dis (20.97 M randomly ordered cells -> 0.25 deg, 4 inverse-distance links per cell) at
+    full size: the compact path is chosen for 48 steps, constants are preserved (weights of a
+    cell sum to 1), results lie between the extremes of the linked sources, compact == direct
+    gathers, and a NaN source poisons exactly the cells linked to it."""
+    import torch
+    from smmregrid_b200 import Regridder, synth
+    w = synth.config_weights("C5dis")
+    rg = Regridder(weights=w, remap_area_min=0.0)
+    assert rg.weights_matrix.info()["kernel_name"] == "gather" and rg.n_src == 20971520
+    B = 48
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = 280 + 20 * torch.randn((B, rg.n_src), generator=g, device="cuda", dtype=torch.float32)
+    n0 = smm_lib.smm_launch_count()
+    y = rg.regrid(x).reshape(B, -1)
+    assert smm_lib.smm_launch_count() - n0 == 2                    # two passes, one chunk of <= 64 steps
+    rg.weights_matrix.set_kernel("gather")
+    yg = rg.regrid(x).reshape(B, -1)
+    rg.weights_matrix.set_kernel(None)
+    assert torch.allclose(y, yg, rtol=1e-12, atol=0) and not torch.isnan(y).any()
+    yc = rg.regrid(torch.full((16, rg.n_src), 3.25, device="cuda", dtype=torch.float64)).reshape(16, -1)
+    assert torch.allclose(yc, torch.full_like(yc, 3.25), rtol=1e-13, atol=0)
+    src = torch.from_numpy(np.asarray(w["src_address"]).astype(np.int64) - 1).cuda().reshape(-1, 4)
+    dst = torch.from_numpy(np.asarray(w["dst_address"]).astype(np.int64) - 1).cuda().reshape(-1, 4)
+    assert (dst == dst[:, :1]).all()                                # 4 consecutive links per destination cell
+    xs = x[0].double()[src]
+    lo, hi = xs.min(1).values, xs.max(1).values
+    assert ((y[0][dst[:, 0]] >= lo - 1e-9) & (y[0][dst[:, 0]] <= hi + 1e-9)).all()
+    # one missing source cell -> NaN exactly in the destination cells linked to it (1e20 fill, > 1e19 rule
+    # needs weight > 0.1; smaller weights leak a huge finite value instead, as in the reference)
+    c = int(src[12345, 0])
+    x[3, c] = float("nan")
+    y3 = rg.regrid(x[3:4]).reshape(-1)
+    wts = torch.from_numpy(np.asarray(w["remap_matrix"])[:, 0]).cuda().reshape(-1, 4)
+    hit = (src == c)
+    big = (hit & (wts > 0.1)).any(1)
+    assert torch.isnan(y3[dst[big, 0]]).all() and big.any()
+    untouched = ~hit.any(1)
+    assert torch.allclose(y3[dst[untouched, 0]], y[3][dst[untouched, 0]], rtol=1e-12, atol=0)   # (direct gathers at B = 1)
