@@ -296,3 +296,42 @@ def test_compact_plan_of_scattered_operator(smm_lib):
             assert c.size == ((np.unique(col) // 256) == i).sum()
     finally:
         smm_lib.smm_host_plan_free(h)
+
+
+@pytest.mark.parametrize("pattern", ["all16", "all0_but_one", "alt_1_13", "ramp", "five_everywhere"])
+def test_packed_rows_corner_cases(smm_lib, oracle, pattern):
+    """Packing corner cases: one row per thread (16 links), almost empty operators, rows whose
+    sub-row counts do not divide a thread's four sub-rows, more rows than one tile holds."""
+    rng = np.random.default_rng(len(pattern))
+    n_dst = 2600                                       # > 1024 rows: several tiles even with 4 rows per thread
+    counts = {"all16": np.full(n_dst, 16), "all0_but_one": np.zeros(n_dst, np.int64),
+              "alt_1_13": np.where(np.arange(n_dst) % 2 == 0, 1, 13), "ramp": np.arange(n_dst) % 17,
+              "five_everywhere": np.full(n_dst, 5)}[pattern]
+    if pattern == "all0_but_one":
+        counts[1234] = 3
+    n_src = 40 * 1024
+    dst = np.repeat(np.arange(n_dst), counts)
+    within = np.concatenate([np.arange(c) for c in counts]) if dst.size else np.zeros(0, np.int64)
+    src = np.clip((dst * n_src) // n_dst + 2 * within + rng.integers(0, 2, size=dst.size), 0, n_src - 1)
+    w = rng.random((dst.size, 1)) + 0.1
+    p = HostPlan(smm_lib, src + 1, dst + 1, w, n_src, n_dst)
+    if pattern == "all0_but_one":          # three links in all: not worth staging, the gather kernel serves it
+        assert p.info["kernel_name"] == "gather" and p.info["nnz"] == 3
+        return
+    assert p.info["kernel_name"] == "staged" and p.info["packed_rows"] == 1, p.info
+    _check_plan_invariants(p, n_src)
+    rs = p.rowslot
+    assert np.array_equal(np.sort(rs[rs >= 0]), np.arange(n_dst))
+    need = np.maximum(1, -(-np.diff(p.rowptr) // 4))
+    assert (rs == -2).sum() == (need - 1).sum()
+    # a continuation always follows its row inside the same thread
+    for u in (1, 2, 3):
+        cont = rs[:, u] == -2
+        assert ((rs[:, u - 1] >= 0) | (rs[:, u - 1] == -2))[cont].all()
+    if pattern == "all16":
+        assert p.info["n_tiles"] == -(-n_dst // 256)     # one row per thread
+    if pattern == "five_everywhere":
+        assert p.info["n_tiles"] == -(-n_dst // 512)     # two rows (2 + 2 sub-rows) per thread
+    mat = oracle.compute_weights_matrix_c(src + 1, dst + 1, w, n_src, n_dst)
+    x = rng.standard_normal((2, n_src)) + 2
+    assert_parity(p.emulate(x), oracle.apply_weights_c(x, mat, None, None, 0.0, False), 1e-12, pattern)
