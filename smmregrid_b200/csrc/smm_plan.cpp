@@ -281,8 +281,7 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
         std::vector<std::vector<Link>> bucket(32 * 32);
         int remaining[32];
         int32_t rep_any[32];                         // some link of the row slot (padding when a slot places nothing)
-        auto reset_warp = [&]() {
-            for (auto &bk : bucket) bk.clear();
+        auto reset_warp = [&]() {      // (the buckets are empty: a completed placement drains them)
             for (int i = 0; i < 32; ++i) { rep_any[i] = -1; remaining[i] = 0; }
         };
         auto add_link = [&](int slot, uint32_t li, double w) {
@@ -332,22 +331,25 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
             auto run_matching = [&](bool cosched, std::vector<uint16_t> &o_li, std::vector<double> &o_w,
                                     std::vector<uint8_t> &o_have) -> bool {
             // (re)fill the per-bank buckets from the row pools; descending, so pop_back ascends
-            for (auto &bk : bucket) bk.clear();
+            for (int jr = 0; jr < rows_in_warp; ++jr)
+                for (const Link &l : pool[jr]) bucket[static_cast<size_t>(jr) * 32 + (l.li & 31u)].clear();
             for (int jr = 0; jr < rows_in_warp; ++jr) {
                 remaining[jr] = static_cast<int>(pool[jr].size());
                 for (size_t j = pool[jr].size(); j-- > 0;)
                     bucket[static_cast<size_t>(jr) * 32 + (pool[jr][j].li & 31u)].push_back(pool[jr][j]);
             }
             for (int k = 0; k < nslots; ++k) {
-                uint32_t cand[32];
+                uint32_t cand[32], rowmask[32];
                 int order[32], ncand[32];
-                for (int lane = 0; lane < 32; ++lane) {
-                    const int jr = lane / lpr_;
+                for (int jr = 0; jr < rows_in_warp; ++jr) {      // banks in which the row still has links
                     uint32_t m = 0;
-                    for (int b = 0; b < 32; ++b)
-                        if (!bucket[static_cast<size_t>(jr) * 32 + b].empty()) m |= 1u << b;
-                    cand[lane] = m;
-                    ncand[lane] = __builtin_popcount(m);
+                    for (const Link &l : pool[jr])
+                        if (!bucket[static_cast<size_t>(jr) * 32 + (l.li & 31u)].empty()) m |= 1u << (l.li & 31u);
+                    rowmask[jr] = m;
+                }
+                for (int lane = 0; lane < 32; ++lane) {
+                    cand[lane] = rowmask[lane / lpr_];
+                    ncand[lane] = __builtin_popcount(cand[lane]);
                     order[lane] = lane;
                 }
                 std::stable_sort(order, order + 32, [&](int x, int y) { return ncand[x] < ncand[y]; });
@@ -360,20 +362,25 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
                 for (int jr = 0; jr < rows_in_warp; ++jr) quota[jr] = remaining[jr];
                 // banks are tried fullest first, so a row drains its banks evenly and the later
                 // slots still have a choice
-                uint8_t pref[32][32];
+                uint8_t pref[32][32], npref[32];          // a row's non-empty banks: fullest first, then by bank
                 for (int jr = 0; jr < rows_in_warp; ++jr) {
                     uint8_t *pr = pref[jr];
-                    for (int b = 0; b < 32; ++b) pr[b] = static_cast<uint8_t>(b);
                     const size_t base = static_cast<size_t>(jr) * 32;
-                    std::stable_sort(pr, pr + 32, [&](uint8_t x, uint8_t y) {
-                        return bucket[base + x].size() > bucket[base + y].size();
-                    });
+                    int n = 0;
+                    for (uint32_t m = rowmask[jr]; m; m &= m - 1) {
+                        const int b = __builtin_ctz(m);
+                        const size_t sz = bucket[base + b].size();
+                        int at = n++;
+                        while (at > 0 && bucket[base + pr[at - 1]].size() < sz) { pr[at] = pr[at - 1]; --at; }
+                        pr[at] = static_cast<uint8_t>(b);
+                    }
+                    npref[jr] = static_cast<uint8_t>(n);
                 }
                 auto augment = [&](auto &&self, int lane, uint32_t &seen) -> bool {
                     const uint8_t *pr = pref[lane / lpr_];
-                    for (int i = 0; i < 32; ++i) {
+                    const int n = npref[lane / lpr_];
+                    for (int i = 0; i < n; ++i) {
                         const int b = pr[i];
-                        if (!((cand[lane] >> b) & 1u)) break;          // sorted by size: the rest is empty
                         if ((seen >> b) & 1u) continue;
                         seen |= 1u << b;
                         if (owner[b] < 0 || self(self, owner[b], seen)) { owner[b] = lane; return true; }
