@@ -206,6 +206,12 @@ PlanChoice choose_plan(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_c
     return pc;
 }
 
+int host_threads_all()
+{
+    cpu_set_t set;
+    return sched_getaffinity(0, sizeof(set), &set) == 0 ? std::max(1, CPU_COUNT(&set)) : 1;
+}
+
 // Tile plans of all levels.  A packed tile holds 4x the rows, so its footprint may not fit where
 // the lane-per-row tile's does: if any level's packed plan is unusable, all levels fall back to
 // the lane-per-row layout (one kernel per grouped launch).
@@ -214,12 +220,7 @@ void plan_levels(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, 
     PlanChoice pc = choose_plan(csrs, n_dst, sm_count);
     plans.assign(csrs.size(), HostPlan{});
     // levels are independent: a few host threads take them in turn (75 ocean levels: ~13 s -> ~1 s)
-    int nthreads = 1;
-    {
-        cpu_set_t set;
-        if (sched_getaffinity(0, sizeof(set), &set) == 0) nthreads = CPU_COUNT(&set);
-        nthreads = std::max(1, std::min({nthreads, 16, static_cast<int>(csrs.size())}));
-    }
+    const int nthreads = std::max(1, std::min({host_threads_all(), 16, static_cast<int>(csrs.size())}));
     for (int pass = 0; pass < 2; ++pass) {
         std::atomic<size_t> next{0};
         std::atomic<bool> retry{false};
@@ -762,14 +763,33 @@ int smm_create_levels(int32_t n_levels, const int64_t *link_length, int64_t nl_m
     if (rc) { delete h; return rc; }
 
     std::vector<HostCsr> csrs(static_cast<size_t>(n_levels));
-    std::string err;
-    for (int32_t i = 0; i < n_levels; ++i) {
-        const int64_t o = static_cast<int64_t>(i) * nl_max;
-        rc = build_csr(n_src, n_dst, link_length[i], src_address ? src_address + o : nullptr,
-                       dst_address ? dst_address + o : nullptr,
-                       remap_matrix ? remap_matrix + o * num_wgts : nullptr, num_wgts, index_base,
-                       csrs[i], err);
-        if (rc) { delete h; return fail(rc, (n_levels > 1 ? "level " + std::to_string(i) + ": " : "") + err); }
+    {
+        // levels are independent: built by a few host threads; the first failing level is reported
+        std::vector<int> rcs(static_cast<size_t>(n_levels), SMM_OK);
+        std::vector<std::string> errs(static_cast<size_t>(n_levels));
+        std::atomic<int32_t> next{0};
+        auto work = [&]() {
+            for (int32_t i = next.fetch_add(1); i < n_levels; i = next.fetch_add(1)) {
+                const int64_t o = static_cast<int64_t>(i) * nl_max;
+                rcs[i] = build_csr(n_src, n_dst, link_length[i], src_address ? src_address + o : nullptr,
+                                   dst_address ? dst_address + o : nullptr,
+                                   remap_matrix ? remap_matrix + o * num_wgts : nullptr, num_wgts, index_base,
+                                   csrs[i], errs[i]);
+            }
+        };
+        const int nthreads = std::max(1, std::min({host_threads_all(), 16, static_cast<int>(n_levels)}));
+        if (nthreads == 1) {
+            work();
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthreads; ++t) pool.emplace_back(work);
+            for (auto &th : pool) th.join();
+        }
+        for (int32_t i = 0; i < n_levels; ++i)
+            if (rcs[i]) {
+                delete h;
+                return fail(rcs[i], (n_levels > 1 ? "level " + std::to_string(i) + ": " : "") + errs[i]);
+            }
     }
     std::vector<HostPlan> plans;
     plan_levels(csrs, n_dst, h->sm_count, plans);
