@@ -7,11 +7,17 @@
 //                   evict-first); the consumer warps hold the tile's link weights and
 //                   footprint offsets in REGISTERS for the whole batch loop, so per batch row
 //                   the only HBM traffic is the X stream in and the tile's rows out.  LPR
-//                   lanes share one destination row.
+//                   lanes share one destination row; operators without a row above 16 links
+//                   use the PACKED layout instead (a thread owns up to four rows).
 //   gather_kernel   generic CSR fallback: direct ld.global.nc gathers, kGatherBT batch rows
 //                   register-blocked per thread (scattered sources, oversized rows,
 //                   unaligned slabs).
+//   compact_kernel + compact_apply_kernel
+//                   two-pass alternative to the gathers for scattered sources with enough batch
+//                   rows: touched columns transposed into a compact buffer, then links applied
+//                   with lanes over the batch, in the reference's summation order.
 //   mask_sum_kernel mask_tensordot (weights.py:47-52): sequential ascending-src sum per row.
+//   nan_variation_kernel  detect_nan_variation_dims (util.py:57-85) for one axis.
 //
 // Numerics (smmregrid/regrid.py:544-570): non-finite x -> 1e20 in x's dtype, float64
 // products/accumulation, NaN where dst_grid_imask == 0 / dst_grid_frac < remap_area_min /
