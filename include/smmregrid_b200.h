@@ -12,9 +12,12 @@
  * dst_grid_frac).  Arrays passed to create/set functions are HOST pointers, copied, never
  * retained.  x / y of smm_apply* are DEVICE pointers owned by the caller (smm_apply_host
  * takes HOST pointers and stages them itself).  A handle is immutable after creation
- * except through smm_set_dst_mask / smm_mask_sum; smm_apply* are re-entrant across
- * streams.  There is no CPU fallback: every function fails with SMM_ERR_CUDA when no
- * sm_100 device is usable.
+ * except through smm_set_dst_mask / smm_mask_sum (which must not run concurrently with an
+ * apply on the same level); everything that varies per call -- kernel family, the
+ * renormalising extension -- is an ARGUMENT of smm_apply* (smm_apply_opts), never handle
+ * state, so smm_apply* are re-entrant across threads and streams and one handle can be
+ * shared by any number of callers.  There is no CPU fallback: every function fails with
+ * SMM_ERR_CUDA when no sm_100 device is usable.
  */
 #ifndef SMMREGRID_B200_H
 #define SMMREGRID_B200_H
@@ -43,8 +46,49 @@ extern "C" {
                              /* then applied with lanes over the batch) whatever B is;     */
                              /* by default it is chosen per apply from B and the density   */
 
+/*
+ * Summation order of a destination row's links (smm_create_opts.summation, smm_info.summation).
+ * The reference's matmul loop (pydata/sparse ndarray . COO, reached from
+ * dask.array.tensordot, smmregrid/regrid.py:550) adds a row's products one by one in ascending
+ * source order, each product and each sum rounded once.
+ *   SMM_SUM_REFERENCE  exactly that order: every value is bit-identical to the reference loop.
+ *   SMM_SUM_FAST       lane-split, tree-reduced FMA sums: agree with the reference to rounding
+ *                      of sum |w x| (<= 1e-12 relative whenever the products share one sign);
+ *                      the `> 1e19` decision is still taken on a reference-order replay.
+ *   SMM_SUM_AUTO       REFERENCE when some weight is negative (bicubic, second-order
+ *                      conservative: products cancel), else FAST.
+ */
+#define SMM_SUM_AUTO 0
+#define SMM_SUM_FAST 1
+#define SMM_SUM_REFERENCE 2
+
 typedef struct smm_handle smm_handle;
 typedef void *smm_stream_t; /* cudaStream_t; NULL = legacy default stream */
+
+/* Options of smm_create / smm_create_levels (NULL = all defaults = zero-initialised). */
+typedef struct smm_create_opts {
+    int32_t summation;          /* SMM_SUM_*                                                  */
+    int32_t reserved;
+    const char *plan_cache_dir; /* NULL: none.  Directory of an on-disk cache of the operator */
+                                /* construction (CSR + tile plan), keyed by a hash of the link */
+                                /* arrays: a hit skips the host-side build (C4: 1.6 s -> 0.2 s) */
+} smm_create_opts;
+
+/* Per-call options of smm_apply* (NULL = all defaults = zero-initialised). */
+typedef struct smm_apply_opts {
+    int32_t kernel;             /* 0 = automatic, else force SMM_KERNEL_STAGED (fails if the    */
+                                /* level has no staged plan), SMM_KERNEL_GATHER (direct gathers) */
+                                /* or SMM_KERNEL_COMPACT (two-pass path for gather-family levels) */
+    int32_t renormalize;        /* EXTENSION, 0 = off = reference semantics.  != 0: non-finite   */
+                                /* source values are EXCLUDED instead of filled with 1e20: a     */
+                                /* destination that saw missing sources becomes                  */
+                                /*   sum_valid(w x) * sum_all(w) / sum_valid(w)                  */
+                                /* if |sum_valid(w)| >= min_valid_fraction * |sum_all(w)|, else  */
+                                /* NaN; destinations without missing sources, dst_grid_imask and */
+                                /* dst_grid_frac masking are unchanged and the `> 1e19 -> NaN`   */
+                                /* rule is not used (the reference has no counterpart: README.md:40) */
+    double min_valid_fraction;  /* within [0, 1]; read only when renormalize != 0                */
+} smm_apply_opts;
 
 typedef struct smm_info {
     int64_t n_src, n_dst, nnz;   /* nnz after duplicate links were summed                 */
@@ -60,12 +104,14 @@ typedef struct smm_info {
     int32_t rows_reordered;      /* staged plan tiles rows re-ordered by mean source address */
     int32_t packed_rows;         /* staged plan packs up to 4 short rows per thread (then  */
                                  /* rows_per_tile is the most a tile can hold)             */
-    int32_t reserved;
+    int32_t summation;           /* SMM_SUM_FAST or SMM_SUM_REFERENCE: the order this handle sums in */
     int64_t max_tile_elems;      /* largest staged source footprint of a tile (elements)  */
     int64_t sum_tile_elems;      /* sum of staged footprints: source elements one batch   */
                                  /* row pulls through TMA (>= touched columns)            */
     int64_t touched_src;         /* distinct source columns with >= 1 link                */
     int64_t device_bytes;        /* device memory held for this level                     */
+    int32_t plan_cache_hit;      /* 1: CSR + plan came from smm_create_opts.plan_cache_dir */
+    int32_t reserved;
 } smm_info;
 
 /*
@@ -77,7 +123,7 @@ typedef struct smm_info {
 int smm_create(int64_t n_src, int64_t n_dst, int64_t nnz,
                const int32_t *src_address, const int32_t *dst_address,
                const double *remap_matrix, int32_t num_wgts, int32_t index_base,
-               int32_t device, smm_handle **out);
+               int32_t device, const smm_create_opts *opts, smm_handle **out);
 
 /*
  * compute_weights_matrix3d (smmregrid/weights.py:7-23) on the padded 3-D layout written by
@@ -89,7 +135,7 @@ int smm_create_levels(int32_t n_levels, const int64_t *link_length, int64_t nl_m
                       int64_t n_src, int64_t n_dst,
                       const int32_t *src_address, const int32_t *dst_address,
                       const double *remap_matrix, int32_t num_wgts, int32_t index_base,
-                      int32_t device, smm_handle **out);
+                      int32_t device, const smm_create_opts *opts, smm_handle **out);
 
 /* The reference drops the matrix object; here the handle is released explicitly. */
 int smm_destroy(smm_handle *h);
@@ -110,7 +156,8 @@ int smm_mask_sum(smm_handle *h, int32_t level, const int32_t *src_imask,
 /*
  * Install the per-level epilogue vectors read by apply_weights (smmregrid/regrid.py:506-508):
  * dst_grid_imask [n_dst] int32 (NULL keeps the current one) and dst_grid_frac [n_dst]
- * float64 (NULL keeps the current one).  HOST pointers.
+ * float64 (NULL keeps the current one).  HOST pointers.  Synchronises the device: call it
+ * while no apply on this level is in flight.
  */
 int smm_set_dst_mask(smm_handle *h, int32_t level, const int32_t *dst_grid_imask,
                      const double *dst_grid_frac);
@@ -129,7 +176,8 @@ int smm_set_dst_mask(smm_handle *h, int32_t level, const int32_t *dst_grid_imask
 int smm_apply(const smm_handle *h, int32_t level,
               const void *x, int32_t x_dtype, int64_t B, int64_t ldx,
               void *y, int32_t y_dtype, int64_t ldy,
-              int32_t masked, double remap_area_min, smm_stream_t stream);
+              int32_t masked, double remap_area_min, const smm_apply_opts *opts,
+              smm_stream_t stream);
 
 /*
  * Regridder.regrid3d's level loop (smmregrid/regrid.py:387-410) as ONE grouped launch.
@@ -145,7 +193,8 @@ int smm_apply_levels(const smm_handle *h, int32_t n_sel, const int32_t *level_in
                      int64_t x_batch_stride, int64_t x_level_stride,
                      void *y, int32_t y_dtype,
                      int64_t y_batch_stride, int64_t y_level_stride,
-                     const uint8_t *masked, double remap_area_min, smm_stream_t stream);
+                     const uint8_t *masked, double remap_area_min, const smm_apply_opts *opts,
+                     smm_stream_t stream);
 
 /*
  * smm_apply for HOST buffers: x/y are host pointers (pinned or pageable); the batch axis
@@ -156,7 +205,8 @@ int smm_apply_levels(const smm_handle *h, int32_t n_sel, const int32_t *level_in
 int smm_apply_host(const smm_handle *h, int32_t level,
                    const void *x, int32_t x_dtype, int64_t B, int64_t ldx,
                    void *y, int32_t y_dtype, int64_t ldy,
-                   int32_t masked, double remap_area_min, int64_t chunk_rows);
+                   int32_t masked, double remap_area_min, const smm_apply_opts *opts,
+                   int64_t chunk_rows);
 
 
 /*
@@ -167,7 +217,8 @@ int smm_apply_host(const smm_handle *h, int32_t level,
 int smm_apply_levels_host(const smm_handle *h, int32_t n_sel, const int32_t *level_index,
                           const void *x, int32_t x_dtype, int64_t B,
                           void *y, int32_t y_dtype,
-                          const uint8_t *masked, double remap_area_min, int64_t chunk_rows);
+                          const uint8_t *masked, double remap_area_min, const smm_apply_opts *opts,
+                          int64_t chunk_rows);
 
 /*
  * detect_nan_variation_dims (smmregrid/util.py:57-85), one axis per call: the DEVICE array x is
@@ -192,7 +243,7 @@ typedef struct smm_host_plan smm_host_plan;
 int smm_host_plan_build(int64_t n_src, int64_t n_dst, int64_t nnz,
                         const int32_t *src_address, const int32_t *dst_address,
                         const double *remap_matrix, int32_t num_wgts, int32_t index_base,
-                        smm_host_plan **out);
+                        const smm_create_opts *opts, smm_host_plan **out);
 int smm_host_plan_info(const smm_host_plan *p, smm_info *out, int64_t *n_segs_out);
 int smm_host_plan_copy(const smm_host_plan *p, int32_t *rowptr, int32_t *col, double *val,
                        int32_t *tiles, uint32_t *segs, double *wplan, uint16_t *iplan);
@@ -210,23 +261,14 @@ int smm_host_plan_compact(const smm_host_plan *p, int64_t *n_touched_out, int64_
                           int32_t *tcols, int32_t *blk_ptr, int32_t *rcol);
 void smm_host_plan_free(smm_host_plan *p);
 
-/* Force a kernel family for subsequent applies (testing/benchmark aid): 0 = automatic,
- * SMM_KERNEL_STAGED (fails if the level has no staged plan), SMM_KERNEL_GATHER (direct gathers
- * only) or SMM_KERNEL_COMPACT (two-pass path for every gather-family level). */
-int smm_set_kernel(smm_handle *h, int32_t kernel);
-
 /*
- * EXTENSION, off by default (the reference has no counterpart; its README notes that fields
- * with time-varying missing points are not handled, README.md:40).  With
- * min_valid_fraction >= 0 subsequent applies EXCLUDE non-finite source values instead of
- * filling them with 1e20: a destination whose links see missing sources becomes
- *   sum_valid(w*x) * sum_all(w) / sum_valid(w)   if |sum_valid(w)| >= min_valid_fraction*|sum_all(w)|
- *   NaN                                          otherwise,
- * destinations without missing sources are unchanged, dst_grid_imask / dst_grid_frac masking
- * still applies and the `> 1e19 -> NaN` rule is not used.  A negative value restores the
- * reference semantics.
+ * Bare host<->device copy ceiling of this process's device (measurement aid used by bench.py to
+ * put the end-to-end figure next to what the PCIe link itself sustains): copies `bytes` from
+ * the PINNED host buffer `host` to an internal device buffer (direction 0) or back (1) `reps`
+ * times on one stream and returns the average seconds per copy in *seconds_out.
  */
-int smm_set_renormalize(smm_handle *h, double min_valid_fraction);
+int smm_copy_ceiling(int32_t device, void *host, int64_t bytes, int32_t direction, int32_t reps,
+                     double *seconds_out);
 
 /* Kernels launched by this library in the calling process so far (bench.py gpu_launches). */
 int64_t smm_launch_count(void);

@@ -8,17 +8,21 @@ from __future__ import annotations
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_PKG, "csrc")
 LIB_DIR = os.path.join(_PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsmmregrid_b200.so")
-SOURCES = ["smm_api.cu", "smm_plan.cpp"]
-HEADERS = ["smm_common.h", "smm_kernels.cuh", "smm_plan.h",
+# one translation unit per (x, y) element-type pair of the kernels, compiled in parallel
+SOURCES = ["smm_api.cu", "smm_plan.cpp", "smm_plan_cache.cpp",
+           "smm_inst_f32_f32.cu", "smm_inst_f32_f64.cu", "smm_inst_f64_f32.cu", "smm_inst_f64_f64.cu"]
+HEADERS = ["smm_common.h", "smm_internal.h", "smm_kernels.cuh", "smm_launch.cuh", "smm_plan.h",
            os.path.join("..", "..", "include", "smmregrid_b200.h")]
+OBJ_DIR = os.path.join(_PKG, "build")
 
 NVCC_FLAGS = [
-    "-shared", "-Xcompiler", "-fPIC", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
 ]
@@ -45,13 +49,33 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    extra = ["-Xptxas", "-v"] if verbose else []
+    if os.environ.get("SMM_NVCC_FLAGS"):
+        extra += os.environ["SMM_NVCC_FLAGS"].split()
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        return src, obj, proc.returncode, proc.stdout
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    log = "".join(f"--- {src}\n{out}" for src, _, _, out in results if out)
+    bad = [src for src, _, rc, _ in results if rc != 0]
+    if bad:
+        raise RuntimeError(f"nvcc failed on {bad}:\n" + log)
+    tmp = LIB_PATH + ".tmp"
+    proc = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] +
+                          [obj for _, obj, _, _ in results],
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout)
+        raise RuntimeError("link failed:\n" + proc.stdout)
+    os.replace(tmp, LIB_PATH)
     if verbose:
-        print(proc.stdout)
+        print(log)
     return LIB_PATH
 
 

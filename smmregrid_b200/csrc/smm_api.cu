@@ -15,59 +15,47 @@
 #include <sched.h>
 
 #include "../../include/smmregrid_b200.h"
-#include "smm_kernels.cuh"
+#include "smm_internal.h"
+#include "smm_aux_kernels.cuh"
 #include "smm_plan.h"
 
 using namespace smm;
 
-namespace {
+namespace smm {
 
+// the kernel launchers live in the smm_inst_*.cu translation units
+SMM_DECLARE_LAUNCHERS(extern, float, float)
+SMM_DECLARE_LAUNCHERS(extern, float, double)
+SMM_DECLARE_LAUNCHERS(extern, double, float)
+SMM_DECLARE_LAUNCHERS(extern, double, double)
+
+namespace {
 thread_local std::string g_err;
 std::atomic<int64_t> g_launches{0};
+}  // namespace
 
-int fail(int code, const std::string &msg)
+int smm_fail(int code, const std::string &msg)
 {
     g_err = msg;
     return code;
 }
 
-#define CUDA_TRY(expr)                                                                     \
-    do {                                                                                   \
-        cudaError_t e__ = (expr);                                                          \
-        if (e__ != cudaSuccess)                                                            \
-            return fail(e__ == cudaErrorMemoryAllocation ? SMM_ERR_ALLOC : SMM_ERR_CUDA,   \
-                        std::string(#expr) + ": " + cudaGetErrorString(e__));              \
-    } while (0)
+void smm_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-struct LevelDev {
-    int64_t n_src = 0, n_dst = 0, nnz = 0, touched = 0;
-    int32_t max_row_nnz = 0;
-    int32_t *rowptr = nullptr, *col = nullptr;
-    double *val = nullptr;
-    bool staged = false;
-    std::string why_not_staged;
-    int32_t lpr = 0, kpl = 0, rpt = 0, nct = 0, ntiles = 0, max_segs = 0;
-    int64_t max_elems = 0, sum_elems = 0;
-    TileDesc *tiles = nullptr;
-    Seg *segs = nullptr;
-    double *wplan = nullptr;
-    uint16_t *iplan = nullptr;
-    int32_t *rowmap = nullptr;          // tile slot -> row (re-ordered plans) | packed plans: the rowslot table
-    bool packed = false, reordered = false;
-    int32_t *tcols = nullptr, *blk_ptr = nullptr, *rcol = nullptr;   // compact (two-pass) plan of gather levels
-    int32_t compact_blocks = 0;
-    int32_t *imask = nullptr;
-    double *frac = nullptr;
-    bool has_imask = false, has_frac = false;
-    int64_t device_bytes = 0;
-};
+}  // namespace smm
+
+namespace {
+
+int fail(int code, const std::string &msg) { return smm_fail(code, msg); }
+
+constexpr int kHostSlots = 4;
 
 struct HostSlot {
     void *dx = nullptr, *dy = nullptr;
     size_t cap_x = 0, cap_y = 0;
     void *px = nullptr, *py = nullptr;      // pinned bounce buffers for pageable host arrays
     size_t cap_px = 0, cap_py = 0;
-    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;   // H2D done | apply done | D2H done
 };
 
 }  // namespace
@@ -76,15 +64,16 @@ struct smm_handle {
     int device = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
-    int force_kernel = 0;
-    double renorm_min_valid = -1.0;      // opt-in extension, see smm_set_renormalize
+    bool ref_order = false;              // rows are summed in the reference's order (SMM_SUM_REFERENCE)
+    bool cache_hit = false;              // CSR + plans were read from the on-disk plan cache
     std::vector<LevelDev> levels;
     // stream-ordered pool for the compact path's transposed buffer; keeps its memory between
     // applies (re-mapping ~1 GB per call cost 8 ms against 1.9 ms of kernels), freed with the handle
     mutable std::mutex pool_mu;
     mutable cudaMemPool_t pool = nullptr;
     std::mutex host_mu;
-    HostSlot slots[3];
+    HostSlot slots[kHostSlots];
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;     // host pipeline: H2D | applies | D2H
 };
 
 namespace {
@@ -184,7 +173,7 @@ struct PlanChoice {
     int32_t lpr = 0, kpl = 0, nct = 256;
 };
 
-PlanChoice choose_plan(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count)
+PlanChoice choose_plan(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, bool ref_order)
 {
     PlanChoice pc;
     int32_t max_row = 0;
@@ -202,6 +191,7 @@ PlanChoice choose_plan(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_c
     // SMM_CONSUMER_THREADS override
     pc.nct = pc.packed ? default_consumer_threads(0, 1, sm_count)
                        : default_consumer_threads(n_dst, pc.cfg ? pc.lpr : 0, sm_count);
+    if (ref_order) pc.nct = 256;         // reference-order kernels exist for 256 consumer threads only
     (void)nlev;
     return pc;
 }
@@ -215,9 +205,10 @@ int host_threads_all()
 // Tile plans of all levels.  A packed tile holds 4x the rows, so its footprint may not fit where
 // the lane-per-row tile's does: if any level's packed plan is unusable, all levels fall back to
 // the lane-per-row layout (one kernel per grouped launch).
-void plan_levels(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, std::vector<HostPlan> &plans)
+void plan_levels(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, bool ref_order,
+                 std::vector<HostPlan> &plans)
 {
-    PlanChoice pc = choose_plan(csrs, n_dst, sm_count);
+    PlanChoice pc = choose_plan(csrs, n_dst, sm_count, ref_order);
     plans.assign(csrs.size(), HostPlan{});
     // levels are independent: a few host threads take them in turn (75 ocean levels: ~13 s -> ~1 s)
     const int nthreads = std::max(1, std::min({host_threads_all(), 16, static_cast<int>(csrs.size())}));
@@ -228,7 +219,7 @@ void plan_levels(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, 
             for (size_t i = next.fetch_add(1); i < csrs.size() && !retry.load(); i = next.fetch_add(1)) {
                 plans[i] = HostPlan{};
                 if (!pc.cfg) { plans[i].why = "a destination row has more than 512 links"; continue; }
-                build_plan(csrs[i], pc.packed ? -1 : pc.lpr, pc.kpl, pc.nct, plans[i]);
+                build_plan(csrs[i], pc.packed ? -1 : pc.lpr, pc.kpl, pc.nct, ref_order, plans[i]);
                 // only a footprint that is too large can be cured by smaller tiles
                 if (pc.packed && !plans[i].ok && plans[i].why.rfind("tile footprint", 0) == 0) retry.store(true);
             }
@@ -242,44 +233,86 @@ void plan_levels(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, 
         }
         if (!retry.load()) return;
         pc.packed = false;
-        pc.nct = default_consumer_threads(n_dst, pc.lpr, sm_count);
+        pc.nct = ref_order ? 256 : default_consumer_threads(n_dst, pc.lpr, sm_count);
     }
+}
+
+// SMM_SUM_AUTO: reference order when some weight is negative (the products of a row can cancel)
+bool resolve_ref_order(int32_t summation, const std::vector<HostCsr> &csrs)
+{
+    if (const char *e = std::getenv("SMM_SUMMATION")) {          // experiments: fast | reference
+        if (e[0] == 'f') return false;
+        if (e[0] == 'r') return true;
+    }
+    if (summation == SMM_SUM_REFERENCE) return true;
+    if (summation == SMM_SUM_FAST) return false;
+    for (const HostCsr &c : csrs)
+        if (c.has_negative) return true;
+    return false;
+}
+
+
+// Host side of smm_create_levels, shared with the host-only introspection entry point: CSR and
+// tile plans of every level, through the on-disk cache when a directory is given.
+int build_host_operator(int32_t n_levels, const int64_t *link_length, int64_t nl_max, int64_t n_src, int64_t n_dst,
+                        const int32_t *src_address, const int32_t *dst_address, const double *remap_matrix,
+                        int32_t num_wgts, int32_t index_base, const smm_create_opts *opts, int sm_count,
+                        std::vector<HostCsr> &csrs, std::vector<HostPlan> &plans, bool &ref_order, bool &cache_hit)
+{
+    const int32_t summation = opts ? opts->summation : SMM_SUM_AUTO;
+    if (summation != SMM_SUM_AUTO && summation != SMM_SUM_FAST && summation != SMM_SUM_REFERENCE)
+        return fail(SMM_ERR_INVALID, "smm_create_opts.summation must be SMM_SUM_AUTO, SMM_SUM_FAST or SMM_SUM_REFERENCE");
+    const std::string cache_dir = (opts && opts->plan_cache_dir) ? opts->plan_cache_dir : "";
+    csrs.assign(static_cast<size_t>(n_levels), HostCsr{});
+    plans.clear();
+    cache_hit = false;
+    PlanCacheKey cache_key;
+    bool usable_arrays = true;          // the cache key hashes the arrays: they must be there
+    for (int32_t i = 0; i < n_levels; ++i)
+        if (link_length[i] > 0 && (!src_address || !dst_address || !remap_matrix)) usable_arrays = false;
+    const bool use_cache = !cache_dir.empty() && usable_arrays && n_src > 0 && n_dst > 0 && num_wgts >= 1;
+    if (use_cache) {
+        cache_key = plan_cache_key(n_levels, link_length, nl_max, n_src, n_dst, src_address, dst_address,
+                                   remap_matrix, num_wgts, index_base, summation, sm_count);
+        cache_hit = plan_cache_load(cache_dir, cache_key, n_levels, n_src, n_dst, csrs, plans);
+        if (cache_hit) {
+            ref_order = !plans.empty() && plans[0].ref_order;
+            return SMM_OK;
+        }
+        csrs.assign(static_cast<size_t>(n_levels), HostCsr{});
+    }
+    {
+        // levels are independent: built by a few host threads; the first failing level is reported
+        std::vector<int> rcs(static_cast<size_t>(n_levels), SMM_OK);
+        std::vector<std::string> errs(static_cast<size_t>(n_levels));
+        std::atomic<int32_t> next{0};
+        auto work = [&]() {
+            for (int32_t i = next.fetch_add(1); i < n_levels; i = next.fetch_add(1)) {
+                const int64_t o = static_cast<int64_t>(i) * nl_max;
+                rcs[i] = build_csr(n_src, n_dst, link_length[i], src_address ? src_address + o : nullptr,
+                                   dst_address ? dst_address + o : nullptr,
+                                   remap_matrix ? remap_matrix + o * num_wgts : nullptr, num_wgts, index_base,
+                                   csrs[i], errs[i]);
+            }
+        };
+        const int nthreads = std::max(1, std::min({host_threads_all(), 16, static_cast<int>(n_levels)}));
+        if (nthreads == 1) {
+            work();
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthreads; ++t) pool.emplace_back(work);
+            for (auto &th : pool) th.join();
+        }
+        for (int32_t i = 0; i < n_levels; ++i)
+            if (rcs[i]) return fail(rcs[i], (n_levels > 1 ? "level " + std::to_string(i) + ": " : "") + errs[i]);
+    }
+    ref_order = resolve_ref_order(summation, csrs);
+    plan_levels(csrs, n_dst, sm_count, ref_order, plans);
+    if (use_cache) plan_cache_store(cache_dir, cache_key, csrs, plans);   // best effort
+    return SMM_OK;
 }
 
 // ------------------------------------------------------------------ launch dispatch
-
-constexpr int kMaxDevices = 64;
-
-template <typename TX, typename TY>
-int launch_staged_t(int dev, int lpr, int kpl, int nct, bool packed, dim3 grid, size_t smem, cudaStream_t st,
-                    const JobBatch &jb, const ApplyArgs &a)
-{
-#define SMM_CASE_P(L_, K_, N_, P_)                                                                \
-    if (lpr == L_ && kpl == K_ && nct == N_ && packed == P_) {                                    \
-        auto kfn = staged_kernel<TX, TY, L_, K_, N_, P_>;                                         \
-        /* the opt-in is per kernel and device: raise it only when a launch needs more */         \
-        static std::atomic<size_t> optin[kMaxDevices];                                            \
-        if (dev < 0 || dev >= kMaxDevices || optin[dev].load(std::memory_order_relaxed) < smem) { \
-            CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                          static_cast<int>(smem)));                               \
-            if (dev >= 0 && dev < kMaxDevices) optin[dev].store(smem, std::memory_order_relaxed); \
-        }                                                                                         \
-        kfn<<<grid, N_ + 32 * producer_warps(N_), smem, st>>>(jb, a);                             \
-        CUDA_TRY(cudaGetLastError());                                                             \
-        g_launches.fetch_add(1, std::memory_order_relaxed);                                       \
-        return SMM_OK;                                                                            \
-    }
-#define SMM_CASE_N(L_, K_, N_) SMM_CASE_P(L_, K_, N_, false)
-#define SMM_CASE(L_, K_) SMM_CASE_N(L_, K_, 256) SMM_CASE_N(L_, K_, 512)
-    SMM_CASE_P(1, 16, 256, true) SMM_CASE_P(1, 16, 512, true)
-    SMM_CASE(1, 4) SMM_CASE(2, 4) SMM_CASE(1, 8) SMM_CASE(1, 12) SMM_CASE(1, 16) SMM_CASE(2, 12)
-    SMM_CASE(2, 14) SMM_CASE(2, 16) SMM_CASE(4, 12) SMM_CASE(4, 16) SMM_CASE(8, 12) SMM_CASE(8, 14)
-    SMM_CASE(8, 16) SMM_CASE(16, 16) SMM_CASE(32, 16)
-#undef SMM_CASE
-#undef SMM_CASE_N
-#undef SMM_CASE_P
-    return fail(SMM_ERR_INVALID, "no staged kernel for this lane configuration");
-}
 
 int env_int(const char *name, int dflt)
 {
@@ -287,29 +320,11 @@ int env_int(const char *name, int dflt)
     return e ? std::atoi(e) : dflt;
 }
 
-template <typename TX, typename TY>
-int launch_gather_t(int lpr, dim3 grid, cudaStream_t st, const JobBatch &jb, const ApplyArgs &a)
-{
-    if (lpr == 1) gather_kernel<TX, TY, 1><<<grid, kGatherThreads, 0, st>>>(jb, a);
-    else if (lpr == 4) gather_kernel<TX, TY, 4><<<grid, kGatherThreads, 0, st>>>(jb, a);
-    else gather_kernel<TX, TY, 32><<<grid, kGatherThreads, 0, st>>>(jb, a);
-    CUDA_TRY(cudaGetLastError());
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    return SMM_OK;
-}
-
 #define SMM_DTYPE_DISPATCH(FN, ...)                                                    \
     ((x_dtype == SMM_F32 && y_dtype == SMM_F32)   ? FN<float, float>(__VA_ARGS__)      \
      : (x_dtype == SMM_F32 && y_dtype == SMM_F64) ? FN<float, double>(__VA_ARGS__)     \
      : (x_dtype == SMM_F64 && y_dtype == SMM_F32) ? FN<double, float>(__VA_ARGS__)     \
                                                   : FN<double, double>(__VA_ARGS__))
-
-struct JobSpec {
-    int32_t level;
-    const void *x;
-    void *y;
-    int32_t masked;
-};
 
 // Batch rows per work item.  A work item pays a fixed prologue (its tile's register image,
 // barriers: `prologue_us`) and the launch pays about half an item of tail per wave, so with an
@@ -335,12 +350,32 @@ int64_t pick_chunks(int64_t B, int64_t blocks_total, int64_t slots, double bytes
 
 constexpr int kCompactUnavailable = -1;   // launch_compact: nothing was launched, use the gather kernel
 
-// Two-pass apply of one gather-family level (see compact_kernel): per chunk of <= 64 batch rows,
-// transpose the touched source columns into XT, then apply the links from XT.  XT comes from the
-// stream-ordered allocator, so concurrent applies on other streams stay independent.
-template <typename TX, typename TY>
-int launch_compact_t(const smm_handle *h, const LevelDev &L, const JobSpec &sp, int64_t B, int64_t xbs,
-                     int64_t ybs, double area_min, cudaStream_t st)
+// Per-call options, resolved (smm_apply_opts; NULL = defaults).
+struct ApplyOpts {
+    int kernel = 0;                 // 0 automatic | SMM_KERNEL_*
+    double renorm_min_valid = -1.0; // < 0: reference semantics (fill 1e20)
+};
+
+int resolve_opts(const smm_apply_opts *o, ApplyOpts &out)
+{
+    out = ApplyOpts{};
+    if (!o) return SMM_OK;
+    if (o->kernel != 0 && o->kernel != SMM_KERNEL_STAGED && o->kernel != SMM_KERNEL_GATHER &&
+        o->kernel != SMM_KERNEL_COMPACT)
+        return fail(SMM_ERR_INVALID, "smm_apply_opts.kernel must be 0, SMM_KERNEL_STAGED, SMM_KERNEL_GATHER or SMM_KERNEL_COMPACT");
+    out.kernel = o->kernel;
+    if (o->renormalize) {
+        if (!(o->min_valid_fraction >= 0.0 && o->min_valid_fraction <= 1.0))
+            return fail(SMM_ERR_INVALID, "smm_apply_opts.min_valid_fraction must be within [0, 1]");
+        out.renorm_min_valid = o->min_valid_fraction;
+    }
+    return SMM_OK;
+}
+
+// Two-pass apply of one gather-family level (see compact_kernel).  The transposed buffer XT comes
+// from the handle's stream-ordered pool, so concurrent applies on other streams stay independent.
+int launch_compact(const smm_handle *h, const LevelDev &L, const JobSpec &sp, int32_t x_dtype, int32_t y_dtype,
+                   int64_t B, int64_t xbs, int64_t ybs, double area_min, cudaStream_t st)
 {
     {
         std::lock_guard<std::mutex> lock(h->pool_mu);
@@ -358,50 +393,29 @@ int launch_compact_t(const smm_handle *h, const LevelDev &L, const JobSpec &sp, 
             }
         }
     }
-    TX *xt = nullptr;
-    const size_t xt_bytes = std::max<size_t>(static_cast<size_t>(L.touched), 1) * kCompactBC * sizeof(TX);
-    if (cudaMallocFromPoolAsync(reinterpret_cast<void **>(&xt), xt_bytes, h->pool, st) != cudaSuccess) {
+    void *xt = nullptr;
+    const size_t sx = x_dtype == SMM_F32 ? 4 : 8;
+    const size_t xt_bytes = std::max<size_t>(static_cast<size_t>(L.touched), 1) * kCompactBC * sx;
+    if (cudaMallocFromPoolAsync(&xt, xt_bytes, h->pool, st) != cudaSuccess) {
         cudaGetLastError();
         return kCompactUnavailable;                  // not enough memory for the transposed buffer
     }
-    const size_t smem = static_cast<size_t>(kCompactBC) * (kCompactW + 1) * sizeof(TX);
-    static std::atomic<bool> optin[kMaxDevices];
-    if (h->device >= kMaxDevices || !optin[h->device].load(std::memory_order_relaxed)) {
-        cudaError_t e = cudaFuncSetAttribute(compact_kernel<TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             static_cast<int>(smem));
-        if (e != cudaSuccess) { cudaFreeAsync(xt, st); return fail(SMM_ERR_CUDA, cudaGetErrorString(e)); }
-        if (h->device < kMaxDevices) optin[h->device].store(true, std::memory_order_relaxed);
-    }
-    const unsigned grid2 = static_cast<unsigned>((L.n_dst + kCompactRows - 1) / kCompactRows);
-    cudaError_t e = cudaSuccess;
-    for (int64_t b0 = 0; b0 < B && e == cudaSuccess; b0 += kCompactBC) {
-        const int bc = static_cast<int>(std::min<int64_t>(kCompactBC, B - b0));
-        compact_kernel<TX><<<static_cast<unsigned>(L.compact_blocks), kCompactThreads,
-                             static_cast<size_t>(bc) * (kCompactW + 1) * sizeof(TX), st>>>(
-            static_cast<const TX *>(sp.x) + b0 * xbs, xbs, L.n_src, bc, L.tcols, L.blk_ptr, xt);
-        compact_apply_kernel<TX, TY><<<grid2, kCompactThreads, 0, st>>>(
-            xt, bc, L.rowptr, L.rcol, L.val, L.imask, L.frac, sp.masked, area_min, L.n_dst,
-            static_cast<TY *>(sp.y) + b0 * ybs, ybs);
-        e = cudaGetLastError();
-        g_launches.fetch_add(2, std::memory_order_relaxed);
-    }
+    const int rc = SMM_DTYPE_DISPATCH(launch_compact_t, h->device, L, sp, xt, B, xbs, ybs, area_min, st);
     cudaFreeAsync(xt, st);
-    if (e != cudaSuccess) return fail(SMM_ERR_CUDA, std::string("compact apply: ") + cudaGetErrorString(e));
-    return SMM_OK;
-}
-
-int launch_compact(const smm_handle *h, const LevelDev &L, const JobSpec &sp, int32_t x_dtype, int32_t y_dtype,
-                   int64_t B, int64_t xbs, int64_t ybs, double area_min, cudaStream_t st)
-{
-    return SMM_DTYPE_DISPATCH(launch_compact_t, h, L, sp, B, xbs, ybs, area_min, st);
+    return rc;
 }
 
 int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t x_dtype,
                 int32_t y_dtype, int64_t B, int64_t xbs, int64_t ybs, double area_min,
-                cudaStream_t st)
+                const ApplyOpts &opt, cudaStream_t st)
 {
     if (B == 0 || specs.empty()) return SMM_OK;
     const size_t sx = x_dtype == SMM_F32 ? 4 : 8;
+    const bool ord = h->ref_order;
+    // shared memory a staged launch needs for `nstages` stages of one batch row each
+    auto staged_smem = [&](size_t max_segs, size_t max_elems, size_t nstages) {
+        return kSmemHeader + round_up(max_segs * sizeof(Seg), 128) + nstages * round_up(max_elems * sx, 128);
+    };
     std::vector<JobSpec> staged, gather;
     for (const JobSpec &s : specs) {
         const LevelDev &L = h->levels[s.level];
@@ -411,16 +425,15 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         if (area_min > 0.0 && !L.has_frac)
             return fail(SMM_ERR_INVALID, "remap_area_min > 0 but dst_grid_frac was never set for level " +
                                              std::to_string(s.level));
-        bool ok = L.staged && h->force_kernel != SMM_KERNEL_GATHER;
+        bool ok = L.staged && opt.kernel != SMM_KERNEL_GATHER;
         // the renormalising extension is not implemented for packed-rows plans: gather kernel
-        ok = ok && !(L.packed && h->renorm_min_valid >= 0.0);
+        ok = ok && !(L.packed && opt.renorm_min_valid >= 0.0);
         // TMA bulk copies need 16-byte aligned rows and lengths
         ok = ok && (reinterpret_cast<uintptr_t>(s.x) % 16 == 0) && ((xbs * sx) % 16 == 0) &&
              ((L.n_src * sx) % 16 == 0);
         // at least two stages must fit
-        ok = ok && (kSmemHeader + round_up(static_cast<size_t>(L.max_segs) * sizeof(Seg), 128) +
-                        2 * round_up(static_cast<size_t>(L.max_elems) * sx, 128) <= h->smem_optin);
-        if (!ok && h->force_kernel == SMM_KERNEL_STAGED)
+        ok = ok && staged_smem(L.max_segs, L.max_elems, 2) <= h->smem_optin;
+        if (!ok && opt.kernel == SMM_KERNEL_STAGED)
             return fail(SMM_ERR_INVALID, "staged kernel forced but unavailable for level " +
                                              std::to_string(s.level) + ": " +
                                              (L.staged ? std::string("slab alignment / footprint size")
@@ -430,7 +443,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
 
     ApplyArgs a{};
     a.B = B; a.x_bstride = xbs; a.y_bstride = ybs; a.remap_area_min = area_min;
-    a.renorm_min_valid = h->renorm_min_valid;
+    a.renorm_min_valid = opt.renorm_min_valid;
     // experiment switches are read once per process, not per launch
     static const uint32_t k_debug_flags = static_cast<uint32_t>(env_int("SMM_DEBUG_STREAM_ONLY", 0)) & 3u;
     static const int k_max_stages = std::max(2, env_int("SMM_MAX_STAGES", kMaxStages));
@@ -444,21 +457,24 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         j.x = s.x; j.y = s.y; j.masked = s.masked; j.pad = 0;
     };
 
-    // ---- staged launches, up to kMaxJobs levels at a time
+    // ---- staged launches: up to kMaxJobs levels at a time (balanced when there are more), and a
+    // group is closed early when the segment table of one level and the footprint of another would
+    // not fit two stages TOGETHER (each level fits on its own, see above)
     const size_t staged_groups = (staged.size() + kMaxJobs - 1) / kMaxJobs;
     const size_t staged_per = staged_groups ? (staged.size() + staged_groups - 1) / staged_groups : 1;   // balanced
-    for (size_t g0 = 0; g0 < staged.size(); g0 += staged_per) {
-        const size_t g1 = std::min(staged.size(), g0 + staged_per);
+    for (size_t g0 = 0; g0 < staged.size();) {
+        size_t g1 = g0;
         JobBatch jb{};
         int64_t tiles_total = 0;
         size_t max_segs = 0, max_elems = 0;
         int lpr = 0, kpl = 0, nct = 256;
         bool packed = false;
-        for (size_t g = g0; g < g1; ++g) {
-            const LevelDev &L = h->levels[staged[g].level];
+        for (; g1 < staged.size() && g1 - g0 < staged_per; ++g1) {
+            const LevelDev &L = h->levels[staged[g1].level];
+            const size_t ms = std::max<size_t>(max_segs, L.max_segs), me = std::max<size_t>(max_elems, L.max_elems);
+            if (g1 > g0 && staged_smem(ms, me, 2) > h->smem_optin) break;
+            max_segs = ms; max_elems = me;
             tiles_total += L.ntiles;
-            max_segs = std::max<size_t>(max_segs, L.max_segs);
-            max_elems = std::max<size_t>(max_elems, L.max_elems);
             lpr = L.lpr; kpl = L.kpl; nct = L.nct; packed = L.packed;
             a.n_src = L.n_src; a.n_dst = L.n_dst;
         }
@@ -502,9 +518,10 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
             item += static_cast<int64_t>(j.nblocks) * nchunks;
         }
         if (item > INT32_MAX) return fail(SMM_ERR_INVALID, "too many work items in one launch");
+        g0 = g1;
         if (item == 0) continue;
         const dim3 grid(static_cast<unsigned>(item));
-        const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, h->device, lpr, kpl, nct, packed, grid, smem, st, jb, a);
+        const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, h->device, lpr, kpl, nct, packed, ord, grid, smem, st, jb, a);
         if (rc) return rc;
     }
 
@@ -520,8 +537,8 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
             const double gather_cost = static_cast<double>(L.nnz) * 120.0;
             const double compact_cost = 1.5 * (static_cast<double>(L.n_src) + static_cast<double>(L.touched) +
                                                static_cast<double>(L.nnz)) * static_cast<double>(sx);
-            bool use = L.rcol && h->renorm_min_valid < 0.0 && h->force_kernel != SMM_KERNEL_GATHER;
-            if (h->force_kernel != SMM_KERNEL_COMPACT) use = use && B >= 16 && gather_cost > compact_cost;
+            bool use = L.rcol && opt.renorm_min_valid < 0.0 && opt.kernel != SMM_KERNEL_GATHER;
+            if (opt.kernel != SMM_KERNEL_COMPACT) use = use && B >= 16 && gather_cost > compact_cost;
             if (!use) { plain.push_back(sp); continue; }
             const int rc = launch_compact(h, L, sp, x_dtype, y_dtype, B, xbs, ybs, area_min, st);
             if (rc == kCompactUnavailable) { plain.push_back(sp); continue; }
@@ -541,7 +558,8 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
             a.n_src = L.n_src; a.n_dst = L.n_dst;
         }
         const double avg = rows ? static_cast<double>(nnz) / rows : 0.0;
-        const int lpr = avg <= 2.0 ? 1 : (avg <= 24.0 ? 4 : 32);
+        // reference order: one thread walks a row's links in sequence
+        const int lpr = ord ? 1 : (avg <= 2.0 ? 1 : (avg <= 24.0 ? 4 : 32));
         const int rpb = kGatherThreads / lpr;
         int64_t blocks_total = 0;
         for (size_t g = g0; g < g1; ++g)
@@ -564,7 +582,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         }
         if (item > INT32_MAX) return fail(SMM_ERR_INVALID, "too many work items in one launch");
         const dim3 grid(static_cast<unsigned>(item));
-        const int rc = SMM_DTYPE_DISPATCH(launch_gather_t, lpr, grid, st, jb, a);
+        const int rc = SMM_DTYPE_DISPATCH(launch_gather_t, lpr, ord, grid, st, jb, a);
         if (rc) return rc;
     }
     return SMM_OK;
@@ -635,19 +653,27 @@ namespace {
 // Host <-> device streaming pipeline shared by smm_apply_host and smm_apply_levels_host.
 // A batch row is `row_x` bytes of source (rows `x_stride` bytes apart) and `row_y` bytes of
 // result; `launch(dx, dy, nb, stream)` applies the operator to nb batch rows held contiguously
-// on the device.  Pinned (or registered) host arrays are DMA'd directly.  Pageable arrays --
-// what numpy / xarray hand over -- go through pinned bounce buffers filled by a few host
-// threads, which overlaps the host copy of chunk i+1 with the PCIe transfer and kernel of
-// chunk i (cudaMemcpyAsync straight from pageable memory is synchronous and ~3-5x slower).
+// on the device.
+//
+// Three streams, one per engine: ALL host->device copies go back to back on `s_in` (the PCIe
+// link is the bottleneck of the whole pipeline: it must never wait for a kernel or a
+// device->host copy), the applies run on `s_k`, the (50x smaller) results return on `s_out`;
+// events order the three per chunk, and a ring of kHostSlots device buffers lets the copy of
+// chunk i+1.. proceed while chunk i is applied.  Pinned (or registered) host arrays are DMA'd
+// directly.  Pageable arrays -- what numpy / xarray hand over -- go through pinned bounce buffers
+// filled by a few host threads, which overlaps the host copy of chunk i+1 with the PCIe
+// transfer and kernel of chunk i (cudaMemcpyAsync straight from pageable memory is synchronous
+// and ~3-5x slower).
 template <typename Launch>
 int host_pipeline(smm_handle *h, const void *x, size_t row_x, size_t x_stride, void *y, size_t row_y,
                   size_t y_stride, int64_t B, int64_t chunk_rows, Launch launch)
 {
     const bool x_pinned = is_pinned(x), y_pinned = is_pinned(y);
     if (chunk_rows <= 0) {
-        // ~256 MB of source per chunk for direct DMA (pipeline fill/drain of a few percent on
-        // multi-GB batches), ~64 MB when staging; at least 4 rows; SMM_HOST_CHUNK_MB overrides
-        const int64_t mb = std::max(1, env_int("SMM_HOST_CHUNK_MB", x_pinned ? 256 : 64));
+        // ~128 MB of source per chunk for direct DMA (the fill of the pipeline -- the first chunk's
+        // copy -- is the only part that does not overlap), ~64 MB when staging; at least 4 rows;
+        // SMM_HOST_CHUNK_MB overrides
+        const int64_t mb = std::max(1, env_int("SMM_HOST_CHUNK_MB", x_pinned ? 128 : 64));
         chunk_rows = std::max<int64_t>(4, (mb << 20) / std::max<int64_t>(1, static_cast<int64_t>(row_x)));
     }
     chunk_rows = std::min(chunk_rows, B);
@@ -655,10 +681,13 @@ int host_pipeline(smm_handle *h, const void *x, size_t row_x, size_t x_stride, v
     DeviceGuard g(h->device);
     const size_t need_x = static_cast<size_t>(chunk_rows) * row_x;
     const size_t need_y = static_cast<size_t>(chunk_rows) * row_y;
-    const int nslots = B > chunk_rows ? 3 : 1;
+    const int nslots = static_cast<int>(std::min<int64_t>(kHostSlots, (B + chunk_rows - 1) / chunk_rows));
+    for (cudaStream_t *sp : {&h->s_in, &h->s_k, &h->s_out})
+        if (!*sp) CUDA_TRY(cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking));
     for (int s = 0; s < nslots; ++s) {
         HostSlot &sl = h->slots[s];
-        if (!sl.stream) CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        for (cudaEvent_t *ev : {&sl.ev_in, &sl.ev_k, &sl.ev_out})
+            if (!*ev) CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
         if (sl.cap_x < need_x) {
             cudaFree(sl.dx); sl.dx = nullptr; sl.cap_x = 0;
             CUDA_TRY(cudaMalloc(&sl.dx, need_x));
@@ -681,51 +710,72 @@ int host_pipeline(smm_handle *h, const void *x, size_t row_x, size_t x_stride, v
         }
     }
     const int nthreads = host_threads();
-    struct Pending { char *ys = nullptr; int64_t nb = 0; };
-    Pending pending[3];
-    // drains a slot: waits for its D2H and, when staging, copies the rows out to the caller
+    struct Pending { char *ys = nullptr; int64_t nb = 0; bool used = false; };
+    Pending pending[kHostSlots];
+    // waits for the slot's last result copy and, when staging, hands the rows to the caller
     auto drain = [&](int s) -> int {
-        HostSlot &sl = h->slots[s];
-        CUDA_TRY(cudaStreamSynchronize(sl.stream));
+        if (!pending[s].used) return SMM_OK;
+        CUDA_TRY(cudaEventSynchronize(h->slots[s].ev_out));
         if (!y_pinned && pending[s].nb)
-            parallel_copy_rows(pending[s].ys, y_stride, static_cast<const char *>(sl.py), row_y, row_y,
+            parallel_copy_rows(pending[s].ys, y_stride, static_cast<const char *>(h->slots[s].py), row_y, row_y,
                                pending[s].nb, 1);
         pending[s] = Pending{};
         return SMM_OK;
     };
-    int rc, slot = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += chunk_rows, slot = (slot + 1) % nslots) {
-        const int64_t nb = std::min(chunk_rows, B - b0);
-        HostSlot &sl = h->slots[slot];
-        const char *xs = static_cast<const char *>(x) + static_cast<size_t>(b0) * x_stride;
-        char *ys = static_cast<char *>(y) + static_cast<size_t>(b0) * y_stride;
-        if (!x_pinned || !y_pinned) {
-            // the bounce buffers of this slot are reused: its previous chunk must be complete
-            if ((rc = drain(slot))) return rc;
+    // one chunk through the three streams (a lambda so that every failure below leaves through the
+    // common drain of the streams: queued copies must not outlive the call)
+    auto run = [&]() -> int {
+        int rc, slot = 0;
+        for (int64_t b0 = 0; b0 < B; b0 += chunk_rows, slot = (slot + 1) % nslots) {
+            const int64_t nb = std::min(chunk_rows, B - b0);
+            HostSlot &sl = h->slots[slot];
+            const char *xs = static_cast<const char *>(x) + static_cast<size_t>(b0) * x_stride;
+            char *ys = static_cast<char *>(y) + static_cast<size_t>(b0) * y_stride;
+            const bool reused = pending[slot].used;
+            // the result bounce buffer (or nothing) of this slot's previous chunk goes out first
+            if (!y_pinned && (rc = drain(slot))) return rc;
+            if (reused) CUDA_TRY(cudaStreamWaitEvent(h->s_in, sl.ev_k, 0));      // dx free: its kernel is done
+            if (x_pinned) {
+                if (x_stride == row_x)   // contiguous rows: one linear copy runs at the full PCIe rate
+                    CUDA_TRY(cudaMemcpyAsync(sl.dx, xs, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, h->s_in));
+                else
+                    CUDA_TRY(cudaMemcpy2DAsync(sl.dx, row_x, xs, x_stride, row_x, nb, cudaMemcpyHostToDevice, h->s_in));
+            } else {
+                if (reused) CUDA_TRY(cudaEventSynchronize(sl.ev_in));            // px free: its DMA is done
+                parallel_copy_rows(static_cast<char *>(sl.px), row_x, xs, x_stride, row_x, nb, nthreads);
+                CUDA_TRY(cudaMemcpyAsync(sl.dx, sl.px, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, h->s_in));
+            }
+            CUDA_TRY(cudaEventRecord(sl.ev_in, h->s_in));
+            CUDA_TRY(cudaStreamWaitEvent(h->s_k, sl.ev_in, 0));
+            if (reused) CUDA_TRY(cudaStreamWaitEvent(h->s_k, sl.ev_out, 0));     // dy free: its copy-out is done
+            if ((rc = launch(sl.dx, sl.dy, nb, h->s_k))) return rc;
+            CUDA_TRY(cudaEventRecord(sl.ev_k, h->s_k));
+            CUDA_TRY(cudaStreamWaitEvent(h->s_out, sl.ev_k, 0));
+            if (y_pinned) {
+                if (y_stride == row_y)
+                    CUDA_TRY(cudaMemcpyAsync(ys, sl.dy, static_cast<size_t>(nb) * row_y, cudaMemcpyDeviceToHost, h->s_out));
+                else
+                    CUDA_TRY(cudaMemcpy2DAsync(ys, y_stride, sl.dy, row_y, row_y, nb, cudaMemcpyDeviceToHost, h->s_out));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(sl.py, sl.dy, static_cast<size_t>(nb) * row_y, cudaMemcpyDeviceToHost, h->s_out));
+            }
+            CUDA_TRY(cudaEventRecord(sl.ev_out, h->s_out));
+            pending[slot] = Pending{ys, y_pinned ? 0 : nb, true};
         }
-        if (x_pinned) {
-            // stream order serialises reuse of this slot's device buffers with its previous chunk
-            if (x_stride == row_x)   // contiguous rows: one linear copy runs at the full PCIe rate
-                CUDA_TRY(cudaMemcpyAsync(sl.dx, xs, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, sl.stream));
-            else
-                CUDA_TRY(cudaMemcpy2DAsync(sl.dx, row_x, xs, x_stride, row_x, nb, cudaMemcpyHostToDevice, sl.stream));
-        } else {
-            parallel_copy_rows(static_cast<char *>(sl.px), row_x, xs, x_stride, row_x, nb, nthreads);
-            CUDA_TRY(cudaMemcpyAsync(sl.dx, sl.px, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, sl.stream));
-        }
-        if ((rc = launch(sl.dx, sl.dy, nb, sl.stream))) return rc;
-        if (y_pinned) {
-            if (y_stride == row_y)
-                CUDA_TRY(cudaMemcpyAsync(ys, sl.dy, static_cast<size_t>(nb) * row_y, cudaMemcpyDeviceToHost, sl.stream));
-            else
-                CUDA_TRY(cudaMemcpy2DAsync(ys, y_stride, sl.dy, row_y, row_y, nb, cudaMemcpyDeviceToHost, sl.stream));
-        } else {
-            CUDA_TRY(cudaMemcpyAsync(sl.py, sl.dy, static_cast<size_t>(nb) * row_y, cudaMemcpyDeviceToHost, sl.stream));
-            pending[slot] = Pending{ys, nb};
-        }
+        for (int s = 0; s < nslots; ++s)
+            if ((rc = drain(s))) return rc;
+        return SMM_OK;
+    };
+    const int rc = run();
+    if (rc) {
+        // nothing queued may still touch the caller's buffers (or the bounce buffers) after the
+        // failure has been reported
+        const std::string msg = g_err;
+        cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->s_k); cudaStreamSynchronize(h->s_out);
+        cudaGetLastError();
+        g_err = msg;
+        return rc;
     }
-    for (int s = 0; s < nslots; ++s)
-        if ((rc = drain(s))) return rc;
     return SMM_OK;
 }
 
@@ -737,17 +787,17 @@ extern "C" {
 
 int smm_create(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t *src_address,
                const int32_t *dst_address, const double *remap_matrix, int32_t num_wgts,
-               int32_t index_base, int32_t device, smm_handle **out)
+               int32_t index_base, int32_t device, const smm_create_opts *opts, smm_handle **out)
 {
     const int64_t ll = nnz;
     return smm_create_levels(1, &ll, nnz, n_src, n_dst, src_address, dst_address, remap_matrix,
-                             num_wgts, index_base, device, out);
+                             num_wgts, index_base, device, opts, out);
 }
 
 int smm_create_levels(int32_t n_levels, const int64_t *link_length, int64_t nl_max, int64_t n_src,
                       int64_t n_dst, const int32_t *src_address, const int32_t *dst_address,
                       const double *remap_matrix, int32_t num_wgts, int32_t index_base,
-                      int32_t device, smm_handle **out)
+                      int32_t device, const smm_create_opts *opts, smm_handle **out)
 {
     if (!out) return fail(SMM_ERR_INVALID, "null output handle pointer");
     *out = nullptr;
@@ -762,37 +812,11 @@ int smm_create_levels(int32_t n_levels, const int64_t *link_length, int64_t nl_m
     int rc = open_device(device, h);
     if (rc) { delete h; return rc; }
 
-    std::vector<HostCsr> csrs(static_cast<size_t>(n_levels));
-    {
-        // levels are independent: built by a few host threads; the first failing level is reported
-        std::vector<int> rcs(static_cast<size_t>(n_levels), SMM_OK);
-        std::vector<std::string> errs(static_cast<size_t>(n_levels));
-        std::atomic<int32_t> next{0};
-        auto work = [&]() {
-            for (int32_t i = next.fetch_add(1); i < n_levels; i = next.fetch_add(1)) {
-                const int64_t o = static_cast<int64_t>(i) * nl_max;
-                rcs[i] = build_csr(n_src, n_dst, link_length[i], src_address ? src_address + o : nullptr,
-                                   dst_address ? dst_address + o : nullptr,
-                                   remap_matrix ? remap_matrix + o * num_wgts : nullptr, num_wgts, index_base,
-                                   csrs[i], errs[i]);
-            }
-        };
-        const int nthreads = std::max(1, std::min({host_threads_all(), 16, static_cast<int>(n_levels)}));
-        if (nthreads == 1) {
-            work();
-        } else {
-            std::vector<std::thread> pool;
-            for (int t = 0; t < nthreads; ++t) pool.emplace_back(work);
-            for (auto &th : pool) th.join();
-        }
-        for (int32_t i = 0; i < n_levels; ++i)
-            if (rcs[i]) {
-                delete h;
-                return fail(rcs[i], (n_levels > 1 ? "level " + std::to_string(i) + ": " : "") + errs[i]);
-            }
-    }
+    std::vector<HostCsr> csrs;
     std::vector<HostPlan> plans;
-    plan_levels(csrs, n_dst, h->sm_count, plans);
+    rc = build_host_operator(n_levels, link_length, nl_max, n_src, n_dst, src_address, dst_address, remap_matrix,
+                             num_wgts, index_base, opts, h->sm_count, csrs, plans, h->ref_order, h->cache_hit);
+    if (rc) { delete h; return rc; }
     h->levels.resize(static_cast<size_t>(n_levels));
     DeviceGuard g(device);              // the caller's current device is left as it was
     for (int32_t i = 0; i < n_levels; ++i) {
@@ -815,8 +839,11 @@ int smm_destroy(smm_handle *h)
         for (HostSlot &s : h->slots) {
             cudaFree(s.dx); cudaFree(s.dy);
             cudaFreeHost(s.px); cudaFreeHost(s.py);
-            if (s.stream) cudaStreamDestroy(s.stream);
+            for (cudaEvent_t ev : {s.ev_in, s.ev_k, s.ev_out})
+                if (ev) cudaEventDestroy(ev);
         }
+        for (cudaStream_t st : {h->s_in, h->s_k, h->s_out})
+            if (st) cudaStreamDestroy(st);
     }
     delete h;
     return SMM_OK;
@@ -831,8 +858,9 @@ int smm_get_info(const smm_handle *h, int32_t level, smm_info *out)
     std::memset(out, 0, sizeof(*out));
     out->n_src = L.n_src; out->n_dst = L.n_dst; out->nnz = L.nnz;
     out->n_levels = static_cast<int32_t>(h->levels.size());
-    const bool use_staged = L.staged && h->force_kernel != SMM_KERNEL_GATHER;
-    out->kernel = use_staged ? SMM_KERNEL_STAGED : SMM_KERNEL_GATHER;
+    out->kernel = L.staged ? SMM_KERNEL_STAGED : SMM_KERNEL_GATHER;
+    out->summation = h->ref_order ? SMM_SUM_REFERENCE : SMM_SUM_FAST;
+    out->plan_cache_hit = h->cache_hit ? 1 : 0;
     out->lanes_per_row = L.lpr; out->links_per_lane = L.kpl; out->rows_per_tile = L.rpt;
     out->n_tiles = L.ntiles; out->max_row_nnz = L.max_row_nnz;
     out->max_tile_segments = L.max_segs; out->max_tile_elems = L.max_elems;
@@ -852,6 +880,7 @@ int smm_mask_sum(smm_handle *h, int32_t level, const int32_t *src_imask, int32_t
     if (!src_imask) return fail(SMM_ERR_INVALID, "null src_imask");
     DeviceGuard g(h->device);
     LevelDev &L = h->levels[level];
+    CUDA_TRY(cudaDeviceSynchronize());          // the level's dst_grid_imask is rewritten: no apply may be in flight
     int32_t *d_src = nullptr, *d_flag = nullptr;
     CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&d_src), static_cast<size_t>(L.n_src) * sizeof(int32_t)));
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_flag), sizeof(int32_t));
@@ -916,6 +945,8 @@ int smm_set_dst_mask(smm_handle *h, int32_t level, const int32_t *dst_grid_imask
     if (rc) return rc;
     DeviceGuard g(h->device);
     LevelDev &L = h->levels[level];
+    // applies run on non-blocking streams, which the synchronous copies below do not order against
+    CUDA_TRY(cudaDeviceSynchronize());
     if (dst_grid_imask) {
         CUDA_TRY(cudaMemcpy(L.imask, dst_grid_imask, static_cast<size_t>(L.n_dst) * sizeof(int32_t),
                             cudaMemcpyHostToDevice));
@@ -931,11 +962,13 @@ int smm_set_dst_mask(smm_handle *h, int32_t level, const int32_t *dst_grid_imask
 
 int smm_apply(const smm_handle *h, int32_t level, const void *x, int32_t x_dtype, int64_t B,
               int64_t ldx, void *y, int32_t y_dtype, int64_t ldy, int32_t masked,
-              double remap_area_min, smm_stream_t stream)
+              double remap_area_min, const smm_apply_opts *opts, smm_stream_t stream)
 {
     int rc = check_level(h, level);
     if (rc) return rc;
     if ((rc = check_dtypes(x_dtype, y_dtype))) return rc;
+    ApplyOpts opt;
+    if ((rc = resolve_opts(opts, opt))) return rc;
     if (B < 0) return fail(SMM_ERR_INVALID, "B must be >= 0");
     if (B == 0) return SMM_OK;
     const LevelDev &L = h->levels[level];
@@ -945,18 +978,21 @@ int smm_apply(const smm_handle *h, int32_t level, const void *x, int32_t x_dtype
         return fail(SMM_ERR_INVALID, "The remap_area_min provided must be between 0.0 and 1.0");
     DeviceGuard g(h->device);
     std::vector<JobSpec> specs{JobSpec{level, x, y, masked ? 1 : 0}};
-    return launch_jobs(h, specs, x_dtype, y_dtype, B, ldx, ldy, remap_area_min,
+    return launch_jobs(h, specs, x_dtype, y_dtype, B, ldx, ldy, remap_area_min, opt,
                        static_cast<cudaStream_t>(stream));
 }
 
 int smm_apply_levels(const smm_handle *h, int32_t n_sel, const int32_t *level_index, const void *x,
                      int32_t x_dtype, int64_t B, int64_t x_batch_stride, int64_t x_level_stride,
                      void *y, int32_t y_dtype, int64_t y_batch_stride, int64_t y_level_stride,
-                     const uint8_t *masked, double remap_area_min, smm_stream_t stream)
+                     const uint8_t *masked, double remap_area_min, const smm_apply_opts *opts,
+                     smm_stream_t stream)
 {
     if (!h) return fail(SMM_ERR_INVALID, "null handle");
     int rc;
     if ((rc = check_dtypes(x_dtype, y_dtype))) return rc;
+    ApplyOpts opt;
+    if ((rc = resolve_opts(opts, opt))) return rc;
     if (n_sel < 0 || B < 0) return fail(SMM_ERR_INVALID, "n_sel and B must be >= 0");
     if (n_sel == 0 || B == 0) return SMM_OK;
     if (!level_index || !x || !y) return fail(SMM_ERR_INVALID, "null level_index, x or y");
@@ -975,17 +1011,19 @@ int smm_apply_levels(const smm_handle *h, int32_t n_sel, const int32_t *level_in
         specs.push_back(s);
     }
     DeviceGuard g(h->device);
-    return launch_jobs(h, specs, x_dtype, y_dtype, B, x_batch_stride, y_batch_stride, remap_area_min,
+    return launch_jobs(h, specs, x_dtype, y_dtype, B, x_batch_stride, y_batch_stride, remap_area_min, opt,
                        static_cast<cudaStream_t>(stream));
 }
 
 int smm_apply_host(const smm_handle *hc, int32_t level, const void *x, int32_t x_dtype, int64_t B,
                    int64_t ldx, void *y, int32_t y_dtype, int64_t ldy, int32_t masked,
-                   double remap_area_min, int64_t chunk_rows)
+                   double remap_area_min, const smm_apply_opts *opts, int64_t chunk_rows)
 {
     int rc = check_level(hc, level);
     if (rc) return rc;
     if ((rc = check_dtypes(x_dtype, y_dtype))) return rc;
+    ApplyOpts opt;
+    if ((rc = resolve_opts(opts, opt))) return rc;
     if (B < 0) return fail(SMM_ERR_INVALID, "B must be >= 0");
     if (B == 0) return SMM_OK;
     if (!x || !y) return fail(SMM_ERR_INVALID, "null x or y");
@@ -998,17 +1036,19 @@ int smm_apply_host(const smm_handle *hc, int32_t level, const void *x, int32_t x
     return host_pipeline(h, x, L.n_src * sx, ldx * sx, y, L.n_dst * sy, ldy * sy, B, chunk_rows,
                          [&](void *dx, void *dy, int64_t nb, cudaStream_t st) -> int {
                              std::vector<JobSpec> specs{JobSpec{level, dx, dy, masked ? 1 : 0}};
-                             return launch_jobs(h, specs, x_dtype, y_dtype, nb, L.n_src, L.n_dst, remap_area_min, st);
+                             return launch_jobs(h, specs, x_dtype, y_dtype, nb, L.n_src, L.n_dst, remap_area_min, opt, st);
                          });
 }
 
 int smm_apply_levels_host(const smm_handle *hc, int32_t n_sel, const int32_t *level_index, const void *x,
                           int32_t x_dtype, int64_t B, void *y, int32_t y_dtype, const uint8_t *masked,
-                          double remap_area_min, int64_t chunk_rows)
+                          double remap_area_min, const smm_apply_opts *opts, int64_t chunk_rows)
 {
     if (!hc) return fail(SMM_ERR_INVALID, "null handle");
     int rc;
     if ((rc = check_dtypes(x_dtype, y_dtype))) return rc;
+    ApplyOpts opt;
+    if ((rc = resolve_opts(opts, opt))) return rc;
     if (n_sel < 0 || B < 0) return fail(SMM_ERR_INVALID, "n_sel and B must be >= 0");
     if (n_sel == 0 || B == 0) return SMM_OK;
     if (!level_index || !x || !y) return fail(SMM_ERR_INVALID, "null level_index, x or y");
@@ -1030,7 +1070,7 @@ int smm_apply_levels_host(const smm_handle *hc, int32_t n_sel, const int32_t *le
                                                          static_cast<char *>(dy) + static_cast<size_t>(i) * n_dst * sy,
                                                          masked ? (masked[i] ? 1 : 0) : 0});
                              return launch_jobs(h, specs, x_dtype, y_dtype, nb, static_cast<int64_t>(n_sel) * n_src,
-                                                static_cast<int64_t>(n_sel) * n_dst, remap_area_min, st);
+                                                static_cast<int64_t>(n_sel) * n_dst, remap_area_min, opt, st);
                          });
 }
 
@@ -1039,28 +1079,27 @@ int smm_apply_levels_host(const smm_handle *hc, int32_t n_sel, const int32_t *le
 struct smm_host_plan {
     HostCsr csr;
     HostPlan plan;
+    bool cache_hit = false;
 };
 
 int smm_host_plan_build(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t *src_address,
                         const int32_t *dst_address, const double *remap_matrix, int32_t num_wgts,
-                        int32_t index_base, smm_host_plan **out)
+                        int32_t index_base, const smm_create_opts *opts, smm_host_plan **out)
 {
     if (!out) return fail(SMM_ERR_INVALID, "null output pointer");
     *out = nullptr;
+    if (nnz < 0) return fail(SMM_ERR_INVALID, "smm_create: n_src, n_dst must be > 0, nnz >= 0, num_wgts >= 1");
     smm_host_plan *p = new (std::nothrow) smm_host_plan();
     if (!p) return fail(SMM_ERR_ALLOC, "host allocation failed");
-    std::string err;
-    int rc = build_csr(n_src, n_dst, nnz, src_address, dst_address, remap_matrix, num_wgts,
-                       index_base, p->csr, err);
-    if (rc) { delete p; return fail(rc, err); }
-    {
-        std::vector<HostCsr> one(1);
-        one[0] = std::move(p->csr);
-        std::vector<HostPlan> plans;
-        plan_levels(one, n_dst, 148, plans);
-        p->csr = std::move(one[0]);
-        p->plan = std::move(plans[0]);
-    }
+    std::vector<HostCsr> csrs;
+    std::vector<HostPlan> plans;
+    bool ref_order = false;
+    const int64_t ll = nnz;
+    const int rc = build_host_operator(1, &ll, nnz, n_src, n_dst, src_address, dst_address, remap_matrix, num_wgts,
+                                       index_base, opts, 148, csrs, plans, ref_order, p->cache_hit);
+    if (rc) { delete p; return rc; }
+    p->csr = std::move(csrs[0]);
+    p->plan = std::move(plans[0]);
     *out = p;
     return SMM_OK;
 }
@@ -1081,6 +1120,8 @@ int smm_host_plan_info(const smm_host_plan *p, smm_info *out, int64_t *n_segs_ou
     out->consumer_threads = p->plan.nct;
     out->rows_reordered = (p->plan.ok && p->plan.reordered) ? 1 : 0;
     out->packed_rows = (p->plan.ok && p->plan.packed) ? 1 : 0;
+    out->summation = p->plan.ref_order ? SMM_SUM_REFERENCE : SMM_SUM_FAST;
+    out->plan_cache_hit = p->cache_hit ? 1 : 0;
     out->max_tile_elems = p->plan.max_tile_elems;
     out->sum_tile_elems = p->plan.sum_tile_elems;
     out->touched_src = p->csr.touched_src;
@@ -1135,21 +1176,36 @@ int smm_host_plan_compact(const smm_host_plan *p, int64_t *n_touched_out, int64_
 
 void smm_host_plan_free(smm_host_plan *p) { delete p; }
 
-int smm_set_kernel(smm_handle *h, int32_t kernel)
+int smm_copy_ceiling(int32_t device, void *host, int64_t bytes, int32_t direction, int32_t reps,
+                     double *seconds_out)
 {
-    if (!h) return fail(SMM_ERR_INVALID, "null handle");
-    if (kernel != 0 && kernel != SMM_KERNEL_STAGED && kernel != SMM_KERNEL_GATHER && kernel != SMM_KERNEL_COMPACT)
-        return fail(SMM_ERR_INVALID, "kernel must be 0, SMM_KERNEL_STAGED, SMM_KERNEL_GATHER or SMM_KERNEL_COMPACT");
-    h->force_kernel = kernel;
-    return SMM_OK;
-}
-
-int smm_set_renormalize(smm_handle *h, double min_valid_fraction)
-{
-    if (!h) return fail(SMM_ERR_INVALID, "null handle");
-    if (!(min_valid_fraction < 0.0) && !(min_valid_fraction <= 1.0))
-        return fail(SMM_ERR_INVALID, "min_valid_fraction must be negative (off) or within [0, 1]");
-    h->renorm_min_valid = min_valid_fraction < 0.0 ? -1.0 : min_valid_fraction;
+    if (!host || bytes <= 0 || reps < 1 || !seconds_out || (direction != 0 && direction != 1))
+        return fail(SMM_ERR_INVALID, "smm_copy_ceiling: host buffer, bytes > 0, reps >= 1, direction 0|1 required");
+    if (!is_pinned(host)) return fail(SMM_ERR_INVALID, "smm_copy_ceiling: the host buffer must be pinned");
+    DeviceGuard g(device);
+    void *d = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CUDA_TRY(cudaMalloc(&d, static_cast<size_t>(bytes)));
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    const cudaMemcpyKind kind = direction == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    void *dst = direction == 0 ? d : host;
+    const void *src = direction == 0 ? host : d;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), kind, st);      // warm-up
+    if (e == cudaSuccess) e = cudaEventRecord(e0, st);
+    for (int32_t r = 0; r < reps && e == cudaSuccess; ++r) e = cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), kind, st);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SMM_ERR_CUDA, std::string("smm_copy_ceiling: ") + cudaGetErrorString(e));
+    *seconds_out = 1e-3 * static_cast<double>(ms) / reps;
     return SMM_OK;
 }
 
@@ -1157,6 +1213,6 @@ int64_t smm_launch_count(void) { return g_launches.load(std::memory_order_relaxe
 
 const char *smm_last_error(void) { return g_err.c_str(); }
 
-const char *smm_version(void) { return "smmregrid_b200 0.1.0 (sm_100a)"; }
+const char *smm_version(void) { return "smmregrid_b200 0.2.0 (sm_100a)"; }
 
 }  // extern "C"

@@ -22,6 +22,16 @@ constexpr int kMaxJobs = 128;                       // levels per grouped launch
 constexpr int kGatherThreads = 256;
 constexpr int kGatherBT = 4;                        // batch rows register-blocked by the gather kernel
 
+// compact (two-pass) path of scattered-source levels
+#ifndef SMM_COMPACT_BC
+#define SMM_COMPACT_BC 64
+#endif
+#ifndef SMM_COMPACT_W
+#define SMM_COMPACT_W 256
+#endif
+constexpr int kCompactBC = SMM_COMPACT_BC;          // batch rows per chunk (lanes handle b and b + 32)
+constexpr int kCompactW = SMM_COMPACT_W;            // source columns per pass-1 block
+
 struct Seg {          // one aligned run of source columns, in elements
     uint32_t src;     // first source column
     uint32_t dst;     // offset inside the staged footprint

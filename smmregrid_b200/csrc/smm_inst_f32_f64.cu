@@ -1,0 +1,7 @@
+// smm_inst_f32_f64.cu -- kernel launchers for x = float, y = double (one translation unit per type pair so
+// that the library builds in parallel; see smm_internal.h).
+#include "smm_launch.cuh"
+
+namespace smm {
+SMM_DECLARE_LAUNCHERS(, float, double)
+}  // namespace smm

@@ -16,8 +16,7 @@
 //                   two-pass alternative to the gathers for scattered sources with enough batch
 //                   rows: touched columns transposed into a compact buffer, then links applied
 //                   with lanes over the batch, in the reference's summation order.
-//   mask_sum_kernel mask_tensordot (weights.py:47-52): sequential ascending-src sum per row.
-//   nan_variation_kernel  detect_nan_variation_dims (util.py:57-85) for one axis.
+//   (mask_sum_kernel and nan_variation_kernel, the two init-time kernels, are in smm_aux_kernels.cuh)
 //
 // Numerics (smmregrid/regrid.py:544-570): non-finite x -> 1e20 in x's dtype, float64
 // products/accumulation, NaN where dst_grid_imask == 0 / dst_grid_frac < remap_area_min /
@@ -26,9 +25,18 @@
 // the fill, and whenever a sum is within 1e-9 relative of the 1e19 threshold the row is
 // REPLAYED in the reference's order (ascending src, separate multiply and add) so the NaN
 // decision is bit-identical.
+//
+// Summation order.  The fast sums differ from the reference's by rounding only as long as the
+// products of a row do not cancel.  Operators with weights of both signs (bicubic, second-order
+// conservative) are therefore planned and evaluated in the REFERENCE'S OWN ORDER (template
+// parameter ORD: links in ascending source order, separate multiply and add, one dependent
+// chain per row -- a lane holds a contiguous run of the row's links and hands its partial sum
+// to the next lane), which makes every value bit-identical to the reference loop.  Callers can
+// request that order for any operator (SMM_SUM_REFERENCE), e.g. for fields that change sign.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <cuda/std/type_traits>
 
 #include "smm_common.h"
 
@@ -149,11 +157,11 @@ __device__ __forceinline__ bool near_threshold(double acc) { return fabs(acc - 1
 // Epilogue of one destination value (regrid.py:553-570): imask / frac (folded into `dead`), then
 // `> 1e19 -> NaN`.  One comparison keeps ordinary values on the short path; only sums in the
 // neighbourhood of the threshold are replayed in the reference's summation order (`replay()`).
-template <typename TY, typename Replay>
+template <typename TY, bool ORD = false, typename Replay>
 __device__ __forceinline__ TY finish(double acc, bool dead, Replay replay)
 {
     if (acc > 9.9e18) {
-        if (near_threshold(acc)) acc = replay();
+        if (!ORD && near_threshold(acc)) acc = replay();      // ORD: acc already is the reference-order sum
         if (acc > 1e19) acc = CUDART_NAN;
     }
     return static_cast<TY>(dead ? CUDART_NAN : acc);
@@ -262,6 +270,74 @@ __device__ __forceinline__ void lane_sum4(uint32_t sb, const uint32_t (&off)[16]
     }
 }
 
+// ---- reference-order variants (ORD plans: slot k of lane l holds link l*KPL + k of the row's
+// ascending-source list; padding slots carry weight 0 behind the last link)
+
+// products of one lane's links, each rounded once (no FMA contraction)
+template <typename TX, int KPL, bool kFill>
+__device__ __forceinline__ void lane_products(uint32_t sb, const uint32_t (&off)[KPL], const double (&w)[KPL],
+                                              double (&p)[KPL])
+{
+#pragma unroll
+    for (int k = 0; k < KPL; ++k) {
+        TX v = lds<TX>(sb + off[k]);
+        if (kFill) v = fill_invalid(v);
+        p[k] = __dmul_rn(static_cast<double>(v), w[k]);
+    }
+}
+
+// One dependent chain per row through the LPR lanes of its group, in link order.  Every lane of
+// the group returns the row's sum.
+template <int LPR, int KPL>
+__device__ __forceinline__ double ordered_group_sum(const double (&p)[KPL], int l_in)
+{
+    double acc = 0.0;
+    if constexpr (LPR == 1) {
+#pragma unroll
+        for (int k = 0; k < KPL; ++k) acc = __dadd_rn(acc, p[k]);
+        return acc;
+    } else {
+#pragma unroll 1
+        for (int l = 0; l < LPR; ++l) {
+            if (l_in == l) {
+#pragma unroll
+                for (int k = 0; k < KPL; ++k) acc = __dadd_rn(acc, p[k]);
+            }
+            const double up = __shfl_up_sync(0xffffffffu, acc, 1, LPR);
+            if (l_in == l + 1) acc = up;
+        }
+        return __shfl_sync(0xffffffffu, acc, LPR - 1, LPR);
+    }
+}
+
+template <typename TX, int LPR, int KPL, bool kFill>
+__device__ __forceinline__ double lane_sum_ordered(uint32_t sb, const uint32_t (&off)[KPL], const double (&w)[KPL], int l_in)
+{
+    double p[KPL];
+    lane_products<TX, KPL, kFill>(sb, off, w, p);
+    return ordered_group_sum<LPR, KPL>(p, l_in);
+}
+
+// Packed rows in reference order: the chain of a row runs through its consecutive sub-rows
+// (`cont` bit u: sub-row u continues the row of sub-row u-1); s4[u] = the chain after sub-row u.
+template <typename TX, bool kFill>
+__device__ __forceinline__ void lane_chain4(uint32_t sb, const uint32_t (&off)[16], const double (&w)[16], uint32_t cont,
+                                            double (&s4)[4])
+{
+    double c = 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        c = (cont & (1u << u)) ? c : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            TX v = lds<TX>(sb + off[4 * u + j]);
+            if (kFill) v = fill_invalid(v);
+            c = __dadd_rn(c, __dmul_rn(static_cast<double>(v), w[4 * u + j]));
+        }
+        s4[u] = c;
+    }
+}
+
 // Opt-in renormalising mode (extension, off by default): the sums a lane needs to
 // EXCLUDE non-finite sources instead of filling them: sum of w*x over finite x, sum of w over
 // finite x, sum of all w.
@@ -322,7 +398,7 @@ __host__ __device__ constexpr int consumer_regs(int nct) { return nct == 512 ? S
 // PACKED (LPR = 1, KPL = 16): a thread owns up to four short destination rows, one per 4-link
 // sub-row (a longer row continues into the next sub-rows); job.rowmap then holds
 // [ntiles][4][NCT] = destination row of a sub-row, -1 empty, -2 continuation of the previous one.
-template <typename TX, typename TY, int LPR, int KPL, int NCT, bool PACKED = false>
+template <typename TX, typename TY, int LPR, int KPL, int NCT, bool PACKED = false, bool ORD = false>
 __global__ void __launch_bounds__(NCT + 32 * producer_warps(NCT), NCT == 256 ? 2 : 1)
 staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ ApplyArgs a)
 {
@@ -454,21 +530,33 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
                         const bool probe = !prefer_fill || (n_done & 15u) == 0;
                         ++n_done;
                         if (probe) {
-                            lane_sum4<TX, false>(sb, off, w, s4);
+                            if constexpr (ORD) lane_chain4<TX, false>(sb, off, w, flags, s4);
+                            else lane_sum4<TX, false>(sb, off, w, s4);
                             prefer_fill = __any_sync(0xffffffffu, not_finite((s4[0] + s4[1]) + (s4[2] + s4[3])));
                         }
-                        if (prefer_fill) lane_sum4<TX, true>(sb, off, w, s4);      // one copy of the filled sum
+                        if (prefer_fill) {                                          // one copy of the filled sum
+                            if constexpr (ORD) lane_chain4<TX, true>(sb, off, w, flags, s4);
+                            else lane_sum4<TX, true>(sb, off, w, s4);
+                        }
                     }
                     if (n == nb - 1) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(empty_addr + 8 * s);
                     }
                     // a row's value = its first sub-row + the continuation sub-rows behind it
+                    // (ORD: the chain already ran through the continuation sub-rows; the row's value
+                    // is the chain after its last sub-row)
                     double acc[4];
                     acc[3] = s4[3];
-                    acc[2] = s4[2] + ((flags & 8u) ? acc[3] : 0.0);
-                    acc[1] = s4[1] + ((flags & 4u) ? acc[2] : 0.0);
-                    acc[0] = s4[0] + ((flags & 2u) ? acc[1] : 0.0);
+                    if constexpr (ORD) {
+                        acc[2] = (flags & 8u) ? acc[3] : s4[2];
+                        acc[1] = (flags & 4u) ? acc[2] : s4[1];
+                        acc[0] = (flags & 2u) ? acc[1] : s4[0];
+                    } else {
+                        acc[2] = s4[2] + ((flags & 8u) ? acc[3] : 0.0);
+                        acc[1] = s4[1] + ((flags & 4u) ? acc[2] : 0.0);
+                        acc[0] = s4[0] + ((flags & 2u) ? acc[1] : 0.0);
+                    }
                     // one warp-wide test keeps the threshold logic (finish) off the common path,
                     // which is then four predicated stores
                     // (compared on the high words: 0x43E12C7B'00000000 is just below 9.9e18, NaN counts as hot)
@@ -478,8 +566,8 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             if (rs[u] >= 0)
-                                store_y(yb + rs[u], finish<TY>(acc[u], (flags & (16u << u)) != 0,
-                                                               [&]() { return replay_row<TX>(job.rowptr, job.col, job.val, rs[u], xp); }));
+                                store_y(yb + rs[u], finish<TY, ORD>(acc[u], (flags & (16u << u)) != 0,
+                                                                    [&]() { return replay_row<TX>(job.rowptr, job.col, job.val, rs[u], xp); }));
                         }
                     } else {
 #pragma unroll
@@ -524,14 +612,18 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
                     // following ones and re-probes the cheap path every 16 rows.
                     const bool probe = !prefer_fill || (n_done & 15u) == 0;
                     ++n_done;
+                    auto row_sum = [&](auto fill) -> double {        // ORD: already the whole row's sum
+                        if constexpr (ORD) return lane_sum_ordered<TX, LPR, KPL, decltype(fill)::value>(sb, off, w, l_in);
+                        else return lane_sum<TX, KPL, decltype(fill)::value>(sb, off, w);
+                    };
                     if (!probe) {
-                        acc = lane_sum<TX, KPL, true>(sb, off, w);
+                        acc = row_sum(cuda::std::true_type{});
                     } else {
                         prefer_fill = false;
-                        acc = lane_sum<TX, KPL, false>(sb, off, w);
+                        acc = row_sum(cuda::std::false_type{});
                         if (__any_sync(0xffffffffu, not_finite(acc))) {
                             if (a.renorm_min_valid < 0.0) {
-                                acc = lane_sum<TX, KPL, true>(sb, off, w);
+                                acc = row_sum(cuda::std::true_type{});
                                 prefer_fill = true;
                             } else {
                                 double s3[3];
@@ -551,10 +643,10 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
                 if (renormed) {
                     if (l_in == 0 && valid) store_y(yp, static_cast<TY>(dead ? CUDART_NAN : acc));
                 } else {
-                    acc = group_sum<LPR>(acc);
+                    if constexpr (!ORD) acc = group_sum<LPR>(acc);
                     if (l_in == 0 && valid && !(a.debug_flags & 2u)) {       // bit 1 (profiling aid): no stores
                         if (a.renorm_min_valid < 0.0)
-                            store_y(yp, finish<TY>(acc, dead, [&]() { return replay_row<TX>(job.rowptr, job.col, job.val, row, xp); }));
+                            store_y(yp, finish<TY, ORD>(acc, dead, [&]() { return replay_row<TX>(job.rowptr, job.col, job.val, row, xp); }));
                         else
                             store_y(yp, static_cast<TY>(dead ? CUDART_NAN : acc));      // no fill, so no 1e19 rule
                     }
@@ -567,7 +659,9 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
 
 // ------------------------------------------------------------------ gather kernel
 
-template <typename TX, typename TY, int LPR>
+// ORD (always with LPR = 1): a thread walks its row's links in ascending source order with
+// separate multiply and add -- the reference's own summation order.
+template <typename TX, typename TY, int LPR, bool ORD = false>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ ApplyArgs a)
 {
@@ -616,8 +710,11 @@ gather_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
 #pragma unroll
             for (int t = 0; t < BT; ++t) v[t] = ld_nc(xr[t] + c);
 #pragma unroll
-            for (int t = 0; t < BT; ++t)   // renormalising mode keeps raw values: a non-finite sum flags the row
-                acc[t] = fma(static_cast<double>(do_fill ? fill_invalid(v[t]) : v[t]), wv, acc[t]);
+            for (int t = 0; t < BT; ++t) {  // renormalising mode keeps raw values: a non-finite sum flags the row
+                const double xv = static_cast<double>(do_fill ? fill_invalid(v[t]) : v[t]);
+                if constexpr (ORD) acc[t] = __dadd_rn(acc[t], __dmul_rn(xv, wv));
+                else acc[t] = fma(xv, wv, acc[t]);
+            }
         }
 #pragma unroll
         for (int t = 0; t < BT; ++t) {
@@ -651,7 +748,7 @@ gather_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
 #pragma unroll
             for (int t = 0; t < BT; ++t) {
                 if (b + t < b1)
-                    yrow[(b + t) * a.y_bstride] = finish<TY>(acc[t], dead, [&]() {
+                    yrow[(b + t) * a.y_bstride] = finish<TY, ORD>(acc[t], dead, [&]() {
                         return replay_row<TX>(job.rowptr, job.col, job.val, row, xr[t]);
                     });
             }
@@ -670,14 +767,6 @@ gather_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
 // (ascending source, separate multiply and add), so the results are bit-identical to a
 // reference-order evaluation and no threshold replay is needed.
 
-#ifndef SMM_COMPACT_BC
-#define SMM_COMPACT_BC 64
-#endif
-#ifndef SMM_COMPACT_W
-#define SMM_COMPACT_W 256
-#endif
-constexpr int kCompactBC = SMM_COMPACT_BC;   // batch rows per chunk (lanes handle b and b + 32)
-constexpr int kCompactW = SMM_COMPACT_W;     // source columns per pass-1 block
 constexpr int kCompactThreads = 256;
 constexpr int kCompactRows = 32;        // destination rows per pass-2 block
 
@@ -756,49 +845,6 @@ compact_apply_kernel(const TX *__restrict__ xt, int bc, const int32_t *__restric
     const int nrows = static_cast<int>((n_dst - row0 < kCompactRows) ? n_dst - row0 : kCompactRows);
     for (int b = warp; b < bc; b += kCompactThreads / 32)
         if (lane < nrows) y[b * y_bstride + row0 + lane] = out[b][lane];
-}
-
-// ------------------------------------------------------------------ mask_tensordot
-
-// weights.py:47-52.  One thread per destination row, links in ascending-src order, separate
-// multiply and add: bit-identical to the reference's accumulation, so `t < 0.5` is too.
-__global__ void mask_sum_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                                const double *__restrict__ val, const int32_t *__restrict__ src_imask,
-                                int32_t *__restrict__ dst_imask, int32_t *__restrict__ any_masked,
-                                int64_t n_dst)
-{
-    const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (row >= n_dst) return;
-    double t = 0.0;
-    const int j1 = rowptr[row + 1];
-    for (int j = rowptr[row]; j < j1; ++j)
-        t = __dadd_rn(t, __dmul_rn(static_cast<double>(src_imask[col[j]]), val[j]));
-    const int32_t m = t < 0.5 ? 0 : 1;
-    dst_imask[row] = m;
-    if (m == 0) atomicOr(any_masked, 1);
-}
-
-// detect_nan_variation_dims (smmregrid/util.py:57-85) for one axis: x viewed as
-// [outer, n_axis, inner]; counts the (outer, inner) positions whose NaN-ness changes somewhere
-// along the axis (`isnull().astype(int8).diff(dim).astype(bool).any(dim).sum()`).  isnull is
-// NaN only: +-inf is not missing.  One thread per position, coalesced over `inner`.
-template <typename TX>
-__global__ void nan_variation_kernel(const TX *__restrict__ x, int64_t outer, int64_t n_axis, int64_t inner,
-                                     unsigned long long *__restrict__ count)
-{
-    const int64_t pos = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    bool varies = false;
-    if (pos < outer * inner) {
-        const int64_t o = pos / inner, i = pos - o * inner;
-        const TX *p = x + o * n_axis * inner + i;
-        const bool first = p[0] != p[0];
-        for (int64_t k = 1; k < n_axis && !varies; ++k) {
-            const TX v = p[k * inner];
-            varies = (v != v) != first;
-        }
-    }
-    const unsigned n = __popc(__ballot_sync(0xffffffffu, varies));
-    if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, static_cast<unsigned long long>(n));
 }
 
 }  // namespace smm

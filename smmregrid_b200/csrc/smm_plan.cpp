@@ -88,6 +88,9 @@ int build_csr(int64_t n_src, int64_t n_dst, int64_t nnz, const int32_t *src_addr
     for (int32_t c : out.col)
         if (!seen[c]) { seen[c] = 1; ++touched; }
     out.touched_src = touched;
+    out.has_negative = false;
+    for (double v : out.val)
+        if (v < 0.0) { out.has_negative = true; break; }
     return SMM_OK;
 }
 
@@ -135,10 +138,11 @@ int32_t default_consumer_threads(int64_t n_dst, int32_t lpr, int32_t sm_count)
 // iterations where the lane-per-row layout would mostly multiply padding.
 constexpr int kSubRows = 4, kSubLinks = 4;
 
-static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct,
-                               const std::vector<int32_t> *order, bool packed, HostPlan &plan)
+static void build_plan_rows(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct,
+                            const std::vector<int32_t> *order, bool packed, bool ref_order, HostPlan &plan)
 {
     plan = HostPlan{};
+    plan.ref_order = ref_order;
     if (nct != 256 && nct != 512) nct = 256;
     int32_t lpr = force_lpr, kpl = force_kpl;
     if (packed) {
@@ -315,6 +319,38 @@ static void build_plan_ordered(const HostCsr &csr, int32_t force_lpr, int32_t fo
             s_li.assign(cells, 0); m_li.assign(cells, 0); c_li.assign(cells, 0);
             s_w.assign(cells, 0.0); m_w.assign(cells, 0.0); c_w.assign(cells, 0.0);
             s_have.assign(cells, 0); m_have.assign(cells, 0); c_have.assign(cells, 0);
+            if (ref_order) {
+                // reference-order plans: no freedom -- lane l of a row holds links [l*nslots, (l+1)*nslots)
+                // of the row's ascending-source list, slot k the k-th of them (the kernel chains them
+                // in exactly that order); the free placements below are for the fast sums only
+                for (int jr = 0; jr < rows_in_warp; ++jr) {
+                    pool[jr].clear();
+                    for (int b = 0; b < 32; ++b) {
+                        auto &bk = bucket[static_cast<size_t>(jr) * 32 + b];
+                        for (const Link &l : bk) pool[jr].push_back(l);
+                        bk.clear();
+                    }
+                    std::sort(pool[jr].begin(), pool[jr].end(), [](const Link &x, const Link &y) { return x.li < y.li; });
+                    for (size_t j = 0; j < pool[jr].size(); ++j) {
+                        const size_t at = (j % nslots) * 32 + static_cast<size_t>(jr) * lpr_ + j / nslots;
+                        s_li[at] = pool[jr][j].li; s_w[at] = pool[jr][j].w; s_have[at] = 1;
+                    }
+                }
+                for (int k = 0; k < nslots; ++k) {
+                    int32_t pad = -1;
+                    for (int lane = 0; lane < 32 && pad < 0; ++lane)
+                        if (s_have[k * 32 + lane]) pad = s_li[k * 32 + lane];
+                    for (int lane = 0; lane < 32 && pad < 0; ++lane)
+                        if (rep_any[lane / lpr_] >= 0) pad = rep_any[lane / lpr_];
+                    if (pad < 0) pad = 0;
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const size_t at = tbase + static_cast<size_t>(slot0 + k) * nct + thread0 + lane;
+                        plan.wplan[at] = s_have[k * 32 + lane] ? s_w[k * 32 + lane] : 0.0;
+                        plan.iplan[at] = s_have[k * 32 + lane] ? s_li[k * 32 + lane] : static_cast<uint16_t>(pad);
+                    }
+                }
+                return true;
+            }
             // in-order alternative: link j of a row slot -> (lane j % lpr_, slot j / lpr_).  It keeps
             // equal addresses of neighbouring rows in the same slot (up-sampling: broadcasts), which
             // the bank matching below cannot see
@@ -628,11 +664,11 @@ bool prefer_packed(int64_t slots_packed)
     return true;
 }
 
-void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, HostPlan &plan)
+void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, bool ref_order, HostPlan &plan)
 {
     const bool packed = force_lpr == -1;       // -1: packed layout requested (see smm_create_levels)
     if (packed) { force_lpr = 0; force_kpl = 0; }
-    build_plan_ordered(csr, force_lpr, force_kpl, nct, nullptr, packed, plan);
+    build_plan_rows(csr, force_lpr, force_kpl, nct, nullptr, packed, ref_order, plan);
     if (plan.lpr == 0 || csr.col.empty()) return;
     // natural order good enough: footprints within 30 % of the columns actually touched
     if (plan.ok && plan_cost(plan) <= 1.3 * static_cast<double>(plan.sum_tile_cols)) return;
@@ -649,7 +685,7 @@ void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return key[x] < key[y]; });
     HostPlan alt;
-    build_plan_ordered(csr, force_lpr, force_kpl, nct, &order, packed, alt);
+    build_plan_rows(csr, force_lpr, force_kpl, nct, &order, packed, ref_order, alt);
     if (alt.ok && (!plan.ok || plan_cost(alt) < 0.8 * plan_cost(plan))) plan = std::move(alt);
 }
 

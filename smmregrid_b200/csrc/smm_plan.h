@@ -17,6 +17,7 @@ struct HostCsr {
     std::vector<double> val;
     int32_t max_row_nnz = 0;
     int64_t touched_src = 0;
+    bool has_negative = false;     // some weight < 0: sums may cancel (bicubic, second-order conservative)
 };
 
 // Compact (two-pass) plan of a level served by the gather family: the touched source columns in
@@ -45,6 +46,7 @@ struct HostPlan {
     std::vector<int32_t> rowmap;   // empty: tile t holds rows [t*R, ...); else destination row of every tile slot
     bool reordered = false;        // rows were tiled in mean-source-address order
     bool packed = false;           // packed-rows plan: one thread owns up to 4 short rows (4 link slots each)
+    bool ref_order = false;        // links placed for reference-order summation (lane l, slot k = link l*kpl + k)
     std::vector<int32_t> rowslot;  // packed: [ntiles][4][nct] destination row of a sub-row, -1 empty, -2 continuation
     std::vector<double> wplan;     // [ntiles][kpl][nct]
     std::vector<uint16_t> iplan;   // [ntiles][kpl][nct]
@@ -65,7 +67,9 @@ bool choose_lanes(int32_t max_row_nnz, int32_t &lpr, int32_t &kpl);
 // their links, which turns locality-preserving unstructured orderings (HEALPix nested, Morton /
 // partition-ordered meshes) into compact per-tile footprints.
 // force_lpr == -1 requests the packed-rows layout (see prefer_packed).
-void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, HostPlan &plan);
+// ref_order: place the links for the reference's summation order (see staged_kernel ORD) instead of
+// the bank-conflict-minimising free placement of the fast sums.
+void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, bool ref_order, HostPlan &plan);
 
 // Packed-rows layout (one thread owns up to 4 short rows): link slots it would spend on `csr`
 // (-1: a row does not fit), and whether to use it.
@@ -76,5 +80,18 @@ bool prefer_packed(int64_t slots_packed);
 // segments: +4 % on C4, +5 % on C2) when that still leaves at least one tile per SM, else 256.
 // SMM_CONSUMER_THREADS=256|512 overrides.
 int32_t default_consumer_threads(int64_t n_dst, int32_t lpr, int32_t sm_count);
+
+// ---- on-disk cache of the operator construction (smm_plan_cache.cpp)
+struct PlanCacheKey { uint64_t h[2] = {0, 0}; };
+// hash of the link arrays (the used part of every level) and of everything else the plans depend on
+PlanCacheKey plan_cache_key(int32_t n_levels, const int64_t *link_length, int64_t nl_max, int64_t n_src,
+                            int64_t n_dst, const int32_t *src_address, const int32_t *dst_address,
+                            const double *remap_matrix, int32_t num_wgts, int32_t index_base,
+                            int32_t summation, int32_t sm_count);
+// false = miss (absent, stale or damaged file): build as usual
+bool plan_cache_load(const std::string &dir, const PlanCacheKey &key, int32_t n_levels, int64_t n_src,
+                     int64_t n_dst, std::vector<HostCsr> &csrs, std::vector<HostPlan> &plans);
+bool plan_cache_store(const std::string &dir, const PlanCacheKey &key, std::vector<HostCsr> &csrs,
+                      std::vector<HostPlan> &plans);
 
 }  // namespace smm

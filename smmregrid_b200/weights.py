@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _lib
 
-LINK_DIMS = ("numLinks", "num_links")          # CDO 2.2.0 renamed it (weights.py:13)
+PLAN_CACHE_ENV = "SMMREGRID_B200_PLAN_CACHE"   # default directory of the on-disk operator cache
 
 
 class CdoWeights:
@@ -65,19 +65,78 @@ class CdoWeights:
 
     @classmethod
     def from_file(cls, path: str, mask_dim=None) -> "CdoWeights":
-        """``.npz`` archive, or netCDF-3 classic via ``scipy.io.netcdf_file`` (netCDF-4 needs
-        xarray + netCDF4, then pass the opened Dataset)."""
+        """Weights file as the reference opens it (``regrid.py:212``, ``cdogenerate.py:296``):
+
+        * ``.npz`` archive written by :meth:`save_npz`;
+        * netCDF-3 (classic / 64-bit offset) through ``scipy.io.netcdf_file``: the links dimension
+          may be ``num_links`` or ``numLinks`` (CDO >= 2.2.0, ``weights.py:13``); for 3-D weights
+          the level dimension is the one ``link_length`` is defined on and its coordinate variable
+          gives the level values used by the nearest-level rule (``regrid.py:386-395``);
+        * netCDF-4 / HDF5 (what ``cdo`` writes by default with ``-f nc4``) needs ``h5py`` or
+          ``netCDF4``; without them convert once with ``cdo -f nc copy`` / ``ncks -3`` (or open
+          the file with xarray where that is installed and pass the Dataset).
+        """
         if path.endswith(".npz"):
             with np.load(path, allow_pickle=False) as z:
                 variables = {k: z[k] for k in z.files if not k.startswith("__attr__")}
                 attrs = {k[len("__attr__"):]: str(z[k]) for k in z.files if k.startswith("__attr__")}
             levels = variables.pop("__levels__", None)
-            return cls(variables, attrs=attrs, mask_dim=mask_dim, levels=levels)
+            md = variables.pop("__mask_dim__", None)
+            return cls(variables, attrs=attrs, mask_dim=mask_dim or (str(md) if md is not None else None),
+                       levels=levels)
+        with open(path, "rb") as f:
+            magic = f.read(8)
+        if magic[:3] == b"CDF":
+            return cls._from_netcdf3(path, mask_dim)
+        if magic == b"\x89HDF\r\n\x1a\n":
+            return cls._from_hdf5(path, mask_dim)
+        raise ValueError(f"{path}: not a .npz archive, a netCDF-3 or a netCDF-4/HDF5 file")
+
+    @classmethod
+    def _from_netcdf3(cls, path, mask_dim):
         from scipy.io import netcdf_file
         with netcdf_file(path, "r", mmap=False) as nc:
             variables = {k: np.array(v[...]) for k, v in nc.variables.items()}
+            dims = {k: tuple(v.dimensions) for k, v in nc.variables.items()}
             attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in nc._attributes.items()}
-        return cls(variables, attrs=attrs, mask_dim=mask_dim)
+        return cls._from_named(variables, dims, attrs, mask_dim)
+
+    @classmethod
+    def _from_hdf5(cls, path, mask_dim):
+        try:
+            import h5py
+        except ImportError as e:
+            raise ImportError(
+                f"{path} is a netCDF-4/HDF5 file and neither h5py nor netCDF4 is installed: convert it "
+                "once with `cdo -f nc copy in.nc out.nc` or `ncks -3 in.nc out.nc`, or open it with "
+                "xarray and pass the Dataset") from e
+        variables, dims = {}, {}
+        with h5py.File(path, "r") as f:
+            for k, v in f.items():
+                if not isinstance(v, h5py.Dataset):
+                    continue
+                is_scale = v.attrs.get("CLASS", b"") == b"DIMENSION_SCALE"
+                if is_scale and str(v.attrs.get("NAME", b"")).find("This is a netCDF dimension but not a netCDF variable") >= 0:
+                    continue                        # a bare dimension, no data
+                variables[k] = np.array(v[...])
+                dims[k] = tuple(d.label or (d.keys()[0] if len(d) else "") for d in v.dims) if not is_scale else (k,)
+            attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in f.attrs.items()
+                     if not k.startswith("_")}
+        return cls._from_named(variables, dims, attrs, mask_dim)
+
+    @classmethod
+    def _from_named(cls, variables, dims, attrs, mask_dim):
+        """Variables with named dimensions -> CdoWeights: the level dimension is the one
+        ``link_length`` lives on, its coordinate variable (if stored) holds the level values."""
+        levels = None
+        md = mask_dim
+        if "link_length" in variables:
+            ldims = dims.get("link_length") or ()
+            md = md or (ldims[0] if ldims and ldims[0] else None)
+            if md and md in variables and variables[md].ndim == 1 and \
+                    variables[md].size == variables["link_length"].size:
+                levels = np.asarray(variables.pop(md), dtype=np.float64)
+        return cls(variables, attrs=attrs, mask_dim=md, levels=levels)
 
     def save_npz(self, path: str):
         out = dict(self.vars)
@@ -85,6 +144,8 @@ class CdoWeights:
             out["__attr__" + k] = np.asarray(str(v))
         if self.levels is not None:
             out["__levels__"] = self.levels
+        if self.mask_dim is not None:
+            out["__mask_dim__"] = np.asarray(str(self.mask_dim))
         np.savez(path, **out)
 
     # --- dataset-like access ----------------------------------------------------------
@@ -191,17 +252,6 @@ class WeightsMatrix:
                 raise ValueError(f"expected {self.shape[1]} destination cells, got {a.size}")
         _lib.check(_lib.load().smm_set_dst_mask(self.handle, level, _ptr(im), _ptr(fr)))
 
-    def set_renormalize(self, min_valid_fraction: Optional[float]):
-        """Opt-in extension (off by default): exclude non-finite sources and renormalise the
-        remaining weights; ``None`` restores the reference's fill-with-1e20 semantics."""
-        v = -1.0 if min_valid_fraction is None else float(min_valid_fraction)
-        _lib.check(_lib.load().smm_set_renormalize(self.handle, v))
-
-    def set_kernel(self, kernel: Optional[str]):
-        code = {None: 0, "auto": 0, "staged": _lib.SMM_KERNEL_STAGED, "gather": _lib.SMM_KERNEL_GATHER,
-                "compact": _lib.SMM_KERNEL_COMPACT}[kernel]
-        _lib.check(_lib.load().smm_set_kernel(self.handle, code))
-
 
 class LevelView:
     def __init__(self, parent: WeightsMatrix, level: int):
@@ -237,10 +287,10 @@ def enable_operator_cache(max_entries: int = 4):
         _CACHE.pop(next(iter(_CACHE)))
 
 
-def _content_key(w: "CdoWeights", device, names):
+def _content_key(w: "CdoWeights", device, names, extra=()):
     import hashlib
     h = hashlib.sha1()
-    h.update(repr((device, w.sizes["src_grid_size"], w.sizes["dst_grid_size"])).encode())
+    h.update(repr((device, w.sizes["src_grid_size"], w.sizes["dst_grid_size"]) + tuple(extra)).encode())
     for name in names:
         a = w.vars.get(name)
         if a is not None:
@@ -250,10 +300,10 @@ def _content_key(w: "CdoWeights", device, names):
     return h.hexdigest()
 
 
-def _cached(w, device, names, build):
+def _cached(w, device, names, build, extra=()):
     if _CACHE_MAX <= 0:
         return build()
-    key = _content_key(w, device, names)
+    key = _content_key(w, device, names, extra)
     wm = _CACHE.pop(key, None)
     if wm is None or not wm._h:
         wm = build()
@@ -263,15 +313,26 @@ def _cached(w, device, names, build):
     return wm
 
 
+# everything that ends up in the device handle: the links, the epilogue vectors, and -- because a
+# weight set WITH a precomputed dst_grid_masked keeps the file's dst_grid_imask while one without
+# has it recomputed from src_grid_imask (regrid.py:196-203) -- the presence and value of that flag
 _KEY_VARS = ("src_address", "dst_address", "remap_matrix", "link_length", "dst_grid_imask", "dst_grid_frac",
-             "src_grid_imask")
+             "src_grid_imask", "dst_grid_masked")
 
 
-def compute_weights_matrix(weights, device=None) -> WeightsMatrix:
+def _plan_cache_dir(plan_cache_dir):
+    import os
+    return plan_cache_dir if plan_cache_dir is not None else (os.environ.get(PLAN_CACHE_ENV) or None)
+
+
+def compute_weights_matrix(weights, device=None, summation=None, plan_cache_dir=None) -> WeightsMatrix:
     """Convert CDO weights to a device operator (reference: ``weights.py:25-44``).
 
     ``src_address - 1``, ``dst_address - 1`` and ``remap_matrix[:, 0]`` become a CSR by
-    destination row; duplicate links are summed as ``sparse.COO`` does.
+    destination row; duplicate links are summed as ``sparse.COO`` does.  ``summation``: None
+    (reference order when a weight is negative, else fast) | 'fast' | 'reference'
+    (``SMM_SUM_*``); ``plan_cache_dir``: on-disk cache of the construction, keyed by a hash of
+    the link arrays (default: ``$SMMREGRID_B200_PLAN_CACHE``).
     """
     w = CdoWeights.from_any(weights)
     src = np.ascontiguousarray(w["src_address"], dtype=np.int32).ravel()
@@ -283,18 +344,20 @@ def compute_weights_matrix(weights, device=None) -> WeightsMatrix:
     n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
     dev = _device_index(device)
 
+    opts = _lib.create_opts(summation, _plan_cache_dir(plan_cache_dir))
+
     def build():
         h = ctypes.c_void_p()
         _lib.check(_lib.load().smm_create(n_src, n_dst, src.size, _ptr(src), _ptr(dst), _ptr(rm),
-                                         num_wgts, 1, dev, ctypes.byref(h)))
+                                         num_wgts, 1, dev, opts, ctypes.byref(h)))
         wm = WeightsMatrix(h, 1, dev, n_src, n_dst)
         _install_masks(wm, w)
         return wm
 
-    return _cached(w, dev, _KEY_VARS, build)
+    return _cached(w, dev, _KEY_VARS, build, extra=(summation,))
 
 
-def compute_weights_matrix3d(weights, mask_dim="lev", device=None) -> WeightsMatrix:
+def compute_weights_matrix3d(weights, mask_dim="lev", device=None, summation=None, plan_cache_dir=None) -> WeightsMatrix:
     """Per-level operators from padded 3-D weights (reference: ``weights.py:7-23``): level i
     uses links ``[0:link_length[i])``."""
     w = CdoWeights.from_any(weights, mask_dim=mask_dim)
@@ -308,15 +371,17 @@ def compute_weights_matrix3d(weights, mask_dim="lev", device=None) -> WeightsMat
     n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
     dev = _device_index(device)
 
+    opts = _lib.create_opts(summation, _plan_cache_dir(plan_cache_dir))
+
     def build():
         h = ctypes.c_void_p()
         _lib.check(_lib.load().smm_create_levels(L, _ptr(ll), nl_max, n_src, n_dst, _ptr(src), _ptr(dst),
-                                                _ptr(rm), num_wgts, 1, dev, ctypes.byref(h)))
+                                                _ptr(rm), num_wgts, 1, dev, opts, ctypes.byref(h)))
         wm = WeightsMatrix(h, L, dev, n_src, n_dst)
         _install_masks(wm, w)
         return wm
 
-    return _cached(w, dev, _KEY_VARS, build)
+    return _cached(w, dev, _KEY_VARS, build, extra=(summation,))
 
 
 def _install_masks(wm: WeightsMatrix, w: CdoWeights):

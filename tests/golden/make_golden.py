@@ -201,7 +201,92 @@ def nan_variation_cases():
     print("nan_variation.npz:", {k: v.tolist() for k, v in out.items() if k.endswith("_dims")})
 
 
+def real_data_case():
+    """The one data file of the reference's own test suite that is readable here (netCDF-3
+    classic): tests/data/tas-healpix2.nc, 12 time steps of near-surface temperature on a HEALPix
+    nside-32 NESTED grid (``cdo setgrid,hp32b_nest``), with the pixel centres.  Stored as a small
+    fixture so that the GPU box can regrid real data (it cannot read /root/reference)."""
+    from scipy.io import netcdf_file
+    with netcdf_file("/root/reference/tests/data/tas-healpix2.nc", "r", mmap=False) as nc:
+        tas = np.array(nc.variables["tas"][...]).astype(np.float32)
+        lat = np.array(nc.variables["lat"][...]).astype(np.float64)
+        lon = np.array(nc.variables["lon"][...]).astype(np.float64)
+        time = np.array(nc.variables["time"][...]).astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, "tas_healpix2.npz"), tas=tas, lat_rad=lat, lon_rad=lon, time=time)
+    print("tas_healpix2.npz:", tas.shape, tas.dtype, float(tas.min()), float(tas.max()))
+
+
+def _coord_record(da, key):
+    c = da.coords[key]
+    return {"dims": list(c.dims), "values": np.asarray(c.data), "attrs": dict(c.attrs)}
+
+
+def dressing_cases():
+    """The xarray side of Regridder.apply_weights (regrid.py:572-626), the reference's own code:
+    output dims, kept coordinates, target lat/lon (remove_degenerate_axes, degrees, rounding),
+    the i/j -> lat/lon swap for regular targets, coordinate and variable attributes -- for a
+    regular, a curvilinear and an unstructured (rank-1) target."""
+    import json
+    rng = np.random.default_rng(5)
+    out = {}
+
+    def record(tag, w, x, dims, coords, attrs):
+        ds = to_dataset(w)
+        matrix = ref_weights.compute_weights_matrix(ds)
+        ds2 = ref_weights.mask_weights(ds, matrix)
+        masked = bool(ref_weights.check_mask(ds2))
+        da = xr.DataArray(x, dims=dims, coords=coords, name="tos", attrs=dict(attrs))
+        res = RefRegridder.apply_weights(_Self(0.5), da, ds2, weights_matrix=matrix, masked=masked,
+                                         horizontal_dims=["lon", "lat", "cell", "i", "j"])
+        meta = {"dims": list(res.dims), "name": res.name, "attrs": dict(res.attrs), "coords": {}}
+        for k in res.coords:
+            rec = _coord_record(res, k)
+            out[f"{tag}_coord_{k}"] = rec["values"]
+            meta["coords"][k] = {"dims": rec["dims"], "attrs": rec["attrs"]}
+        out[f"{tag}_y"] = np.asarray(res.data)
+        out[f"{tag}_x"] = x
+        out[f"{tag}_meta"] = np.asarray(json.dumps(meta))
+        for k, v in inputs_of(w).items():
+            out[f"{tag}_{k}"] = v
+        out[f"{tag}_in_dst_grid_center_lat"] = w["dst_grid_center_lat"]
+        out[f"{tag}_in_dst_grid_center_lon"] = w["dst_grid_center_lon"]
+        print(f"dressing {tag}: dims={meta['dims']} coords={ {k: v['dims'] for k, v in meta['coords'].items()} }")
+
+    attrs = {"units": "K", "long_name": "temperature", "CDI_grid_type": "curvilinear"}
+    # (a) regular target: lat/lon collapse to 1-D and replace i/j
+    w = synth.conservative_latlon(36, 18, 12, 6)
+    x = (280 + 20 * rng.standard_normal((3, 2, 18, 36))).astype(np.float32)
+    record("regular", w, x, ("time", "plev", "lat", "lon"),
+           {"time": np.array([10.0, 20.0, 30.0]), "plev": np.array([85000.0, 50000.0]),
+            "lat": np.linspace(-85, 85, 18), "lon": np.arange(36) * 10.0}, attrs)
+    # (b) curvilinear target: 2-D lat/lon stay on (i, j)
+    v = dict(w.vars)
+    jj, ii = np.meshgrid(np.arange(6), np.arange(12), indexing="ij")
+    v["dst_grid_center_lat"] = np.deg2rad(-75 + 30.0 * jj + 1.5 * ii).ravel()
+    v["dst_grid_center_lon"] = np.deg2rad(15 + 30.0 * ii + 2.0 * jj).ravel()
+    record("curvilinear", synth.CdoWeights(v, attrs=w.attrs), x, ("time", "plev", "lat", "lon"),
+           {"time": np.array([10.0, 20.0, 30.0]), "plev": np.array([85000.0, 50000.0])}, attrs)
+    # (c) unstructured source and target (rank 1): lat/lon on 'cell'
+    n_src, n_dst, nl = 300, 70, 600
+    w1 = synth.CdoWeights({
+        "src_address": rng.integers(1, n_src + 1, nl).astype(np.int32),
+        "dst_address": rng.integers(1, n_dst + 1, nl).astype(np.int32), "remap_matrix": rng.random((nl, 1)),
+        "src_grid_imask": np.ones(n_src, np.int32), "dst_grid_imask": np.ones(n_dst, np.int32),
+        "dst_grid_frac": np.ones(n_dst), "src_grid_dims": np.array([n_src], np.int32),
+        "dst_grid_dims": np.array([n_dst], np.int32),
+        "dst_grid_center_lat": rng.uniform(-1.5, 1.5, n_dst), "dst_grid_center_lon": rng.uniform(0, 6.28, n_dst)},
+        attrs={"source_grid": "unstructured", "dest_grid": "unstructured"})
+    record("cell", w1, rng.standard_normal((4, n_src)), ("time", "cell"), {"time": np.arange(4.0)}, {"units": "1"})
+    np.savez_compressed(os.path.join(HERE, "dressing.npz"), **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) < 2 or sys.argv[1] != "nanvar":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "main"):
         main()
-    nan_variation_cases()
+    if which in ("all", "nanvar"):
+        nan_variation_cases()
+    if which in ("all", "real"):
+        real_data_case()
+    if which in ("all", "dressing"):
+        dressing_cases()

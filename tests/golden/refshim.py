@@ -91,7 +91,7 @@ def _from_delayed(value, shape=None, dtype=None, **_kw):
 
 class DataArray:
     def __init__(self, data=None, dims=None, coords=None, name=None, attrs=None):
-        self.data = None if data is None else np.asarray(data) if not isinstance(data, COO) else data
+        self.data = None if data is None else data if isinstance(data, (COO, FakeDaskArray)) else np.asarray(data)
         self.dims = tuple(dims) if dims is not None else ()
         self.name = name
         self.attrs = dict(attrs or {})
@@ -158,7 +158,19 @@ class DataArray:
         indexers = dict(indexers or {}, **kw)
         key = tuple(indexers.get(d, slice(None)) for d in self.dims)
         dims = [d for d in self.dims if not isinstance(indexers.get(d, slice(None)), (int, np.integer))]
-        return self._new(self.data[key], dims)
+        out = self._new(self.data[key], dims)
+        for k, v in self.coords.items():            # coordinates follow the selection
+            if set(v.dims) <= set(dims):
+                ck = tuple(indexers.get(d, slice(None)) for d in v.dims)
+                out.coords[k] = DataArray(v.data[ck], v.dims, attrs=v.attrs)
+        return out
+
+    def transpose(self, *dims):
+        order = [self.dims.index(d) for d in dims]
+        out = DataArray(np.transpose(self.data, order), dims, name=self.name, attrs=self.attrs)
+        for k, v in self.coords.items():
+            out.coords[k] = v
+        return out
 
     def swap_dims(self, mapping):
         out = DataArray(self.data, [mapping.get(d, d) for d in self.dims], name=self.name, attrs=self.attrs)
@@ -173,7 +185,10 @@ class _Coords(dict):
         self._owner = owner
 
     def __setitem__(self, k, v):
-        if not isinstance(v, DataArray):
+        if isinstance(v, tuple):                    # xarray's (dims, data[, attrs]) form
+            dims = (v[0],) if isinstance(v[0], str) else tuple(v[0])
+            v = DataArray(np.asarray(v[1]), dims, attrs=v[2] if len(v) > 2 else None)
+        elif not isinstance(v, DataArray):
             v = DataArray(np.asarray(v), (k,) if np.ndim(v) == 1 else ())
         super().__setitem__(k, v)
 
@@ -208,6 +223,20 @@ class Dataset:
     @property
     def dims(self): return self.sizes
 
+    @property
+    def data_vars(self): return self.variables
+
+    def map(self, func, keep_attrs=False):
+        out = Dataset(attrs=self.attrs if keep_attrs else None)
+        for k, v in self.variables.items():
+            r = func(v)
+            r.name = k
+            out.variables[k] = r
+        return out
+
+    def drop_vars(self, names):
+        return Dataset({k: v for k, v in self.variables.items() if k not in set(names)}, self.attrs)
+
     def isel(self, indexers=None, **kw):
         indexers = dict(indexers or {}, **kw)
         return Dataset({k: v.isel({d: i for d, i in indexers.items() if d in v.dims})
@@ -218,6 +247,112 @@ class Dataset:
         for k, v in kw.items():
             out[k] = v
         return out
+
+
+# ------------------------------------------------------------- lazy stand-ins (front-end tests)
+
+class LazyDataArray(DataArray):
+    """A DataArray whose backing store is read block by block (like xarray's lazily indexed
+    netCDF variables): every ``.values`` / ``np.asarray`` materialisation is recorded in
+    ``reads`` (bytes) so that a test can bound the peak host memory of the front end."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.reads = []
+
+    @property
+    def values(self):
+        self.reads.append(self.data.nbytes)
+        return self.data
+
+    def _new(self, data, dims=None):
+        out = LazyDataArray(data, self.dims if dims is None else dims, name=self.name, attrs=self.attrs)
+        out.reads = self.reads                       # children report to the root array
+        return out
+
+    def transpose(self, *dims):
+        out = super().transpose(*dims)
+        lazy = LazyDataArray(out.data, out.dims, name=out.name, attrs=out.attrs)
+        for k, v in out.coords.items():
+            lazy.coords[k] = v
+        lazy.reads = self.reads
+        return lazy
+
+
+class FakeDaskArray:
+    """Minimal stand-in for ``dask.array.Array``: numpy data + a chunk structure, evaluated only by
+    ``compute()``.  ``map_blocks`` below records one task per block without running it."""
+
+    def __init__(self, data=None, chunks=None, tasks=None, shape=None, dtype=None):
+        self._data, self.chunks, self._tasks = data, tuple(tuple(c) for c in chunks), tasks
+        self.shape = tuple(sum(c) for c in self.chunks) if shape is None else shape
+        self.dtype = np.dtype(dtype) if dtype is not None else data.dtype
+        self.ndim = len(self.chunks)
+
+    @property
+    def nbytes(self): return int(np.prod(self.shape)) * self.dtype.itemsize
+
+    def rechunk(self, spec):
+        chunks = list(self.chunks)
+        for ax, c in spec.items():
+            chunks[ax] = (self.shape[ax],) if c == -1 else tuple(c)
+        return FakeDaskArray(self._data, chunks, self._tasks, dtype=self.dtype)
+
+    def blocks(self):
+        import itertools
+        starts = [np.concatenate(([0], np.cumsum(c)))[:-1] for c in self.chunks]
+        for idx in itertools.product(*[range(len(c)) for c in self.chunks]):
+            yield idx, tuple(slice(int(starts[a][i]), int(starts[a][i] + self.chunks[a][i])) for a, i in enumerate(idx))
+
+    def compute(self):
+        if self._tasks is None:
+            return self._data
+        out = np.empty(self.shape, self.dtype)
+        for sl, thunk in self._tasks:
+            out[sl] = thunk()
+        return out
+
+    def __array__(self, dtype=None, copy=None):
+        raise AssertionError("a dask-backed field must never be materialised by the front end")
+
+
+FakeDaskArray.__module__ = "dask.array.core"
+
+
+def fake_dask_map_blocks(func, x, dtype=None, chunks=None, drop_axis=(), new_axis=(), meta=None):
+    """``dask.array.map_blocks`` for one input whose dropped axes are single-chunk: builds the
+    output block structure from ``chunks`` and defers ``func`` to ``compute()``."""
+    assert all(len(x.chunks[a]) == 1 for a in drop_axis), "dropped axes must be one chunk"
+    keep = [a for a in range(x.ndim) if a not in set(drop_axis)]
+    out = FakeDaskArray(None, chunks, tasks=[], dtype=dtype)
+    calls = []
+    out_starts = [np.concatenate(([0], np.cumsum(c)))[:-1] for c in out.chunks]
+    for idx, sl in x.blocks():
+        osl, k = [], 0
+        for a in range(out.ndim):
+            if a in set(new_axis):
+                osl.append(slice(0, out.shape[a]))
+            else:
+                i = idx[keep[k]]; k += 1
+                osl.append(slice(int(out_starts[a][i]), int(out_starts[a][i] + out.chunks[a][i])))
+        def thunk(sl=sl):
+            calls.append(sl)
+            return func(np.asarray(x.compute()[sl]) if x._tasks is not None else x._data[sl])
+        out._tasks.append((tuple(osl), thunk))
+    out.calls = calls
+    return out
+
+
+def install_fake_dask():
+    """Register the stand-in as ``dask`` / ``dask.array`` (front-end tests only)."""
+    dask = types.ModuleType("dask")
+    da = types.ModuleType("dask.array")
+    da.Array = FakeDaskArray
+    da.map_blocks = fake_dask_map_blocks
+    da.moveaxis = lambda a, s, d: FakeDaskArray(np.moveaxis(a.compute(), s, d), [(n,) for n in np.moveaxis(np.empty(a.shape, bool), s, d).shape])
+    dask.array = da
+    sys.modules.update({"dask": dask, "dask.array": da})
+    return da
 
 
 # -------------------------------------------------------------------------- installer

@@ -57,7 +57,7 @@ def test_no_cpu_fallback(smm_lib):
     dst = np.array([1, 1], np.int32)
     w = np.array([[0.5], [0.5]])
     h = ctypes.c_void_p()
-    rc = smm_lib.smm_create(2, 1, 2, src.ctypes.data, dst.ctypes.data, w.ctypes.data, 1, 1, 0, ctypes.byref(h))
+    rc = smm_lib.smm_create(2, 1, 2, src.ctypes.data, dst.ctypes.data, w.ctypes.data, 1, 1, 0, None, ctypes.byref(h))
     assert rc == _lib.SMM_ERR_CUDA and not h.value
     assert b"no CPU fallback" in smm_lib.smm_last_error() or b"CUDA" in smm_lib.smm_last_error()
     with pytest.raises(_lib.SmmError):
@@ -78,10 +78,10 @@ def test_argument_validation_without_device(smm_lib):
     from smmregrid_b200 import _lib
     h = ctypes.c_void_p()
     ll = np.array([5], np.int64)
-    rc = smm_lib.smm_create_levels(1, ll.ctypes.data, 3, 4, 4, None, None, None, 1, 1, 0, ctypes.byref(h))
+    rc = smm_lib.smm_create_levels(1, ll.ctypes.data, 3, 4, 4, None, None, None, 1, 1, 0, None, ctypes.byref(h))
     assert rc == _lib.SMM_ERR_INVALID          # link_length > nl_max
-    rc = smm_lib.smm_create_levels(0, ll.ctypes.data, 3, 4, 4, None, None, None, 1, 1, 0, ctypes.byref(h))
+    rc = smm_lib.smm_create_levels(0, ll.ctypes.data, 3, 4, 4, None, None, None, 1, 1, 0, None, ctypes.byref(h))
     assert rc == _lib.SMM_ERR_INVALID
     assert smm_lib.smm_destroy(None) == 0
-    rc = smm_lib.smm_apply(None, 0, None, 0, 1, 1, None, 0, 1, 0, 0.5, None)
+    rc = smm_lib.smm_apply(None, 0, None, 0, 1, 1, None, 0, 1, 0, 0.5, None, None)
     assert rc == _lib.SMM_ERR_INVALID

@@ -32,8 +32,7 @@ def test_golden_2d(smm_lib, cuda, name, kernel):
     from smmregrid_b200 import Regridder
     g = load(name)
     for i, am in enumerate(g["area_mins"]):
-        rg = Regridder(weights=weights_from(g), remap_area_min=float(am))
-        rg.weights_matrix.set_kernel(kernel)
+        rg = Regridder(weights=weights_from(g), remap_area_min=float(am), kernel=kernel)
         assert rg.masked == bool(g["masked"])
         assert np.array_equal(rg.weights["dst_grid_imask"].ravel(), g["dst_grid_imask"].ravel())
         y = rg.regrid(g["in_x"])

@@ -16,18 +16,19 @@ RTOL_F64 = 1e-12
 RTOL_F32 = 1e-6
 
 
-def _create(lib, src, dst, rm, n_src, n_dst):
+def _create(lib, src, dst, rm, n_src, n_dst, summation=None):
     from smmregrid_b200 import _lib
+    opts = _lib.create_opts(summation)
     h = ctypes.c_void_p()
     src = np.ascontiguousarray(src, np.int32)
     dst = np.ascontiguousarray(dst, np.int32)
     rm = np.ascontiguousarray(rm, np.float64)
     _lib.check(lib.smm_create(n_src, n_dst, src.size, src.ctypes.data, dst.ctypes.data, rm.ctypes.data,
-                              rm.shape[1], 1, 0, ctypes.byref(h)))
+                              rm.shape[1], 1, 0, opts, ctypes.byref(h)))
     return h
 
 
-def _apply(lib, h, x_np, n_dst, ydtype, masked, amin, imask=None, frac=None, kernel=0, level=0):
+def _apply(lib, h, x_np, n_dst, ydtype, masked, amin, imask=None, frac=None, kernel=0, level=0, renormalize=None):
     import torch
     from smmregrid_b200 import _lib
     if imask is not None or frac is not None:
@@ -35,12 +36,12 @@ def _apply(lib, h, x_np, n_dst, ydtype, masked, amin, imask=None, frac=None, ker
         fr = None if frac is None else np.ascontiguousarray(frac, np.float64)
         _lib.check(lib.smm_set_dst_mask(h, level, None if im is None else im.ctypes.data,
                                         None if fr is None else fr.ctypes.data))
-    _lib.check(lib.smm_set_kernel(h, kernel))
+    opts = _lib.apply_opts(kernel, renormalize)          # per call: nothing is stored on the handle
     x = torch.from_numpy(x_np).cuda()
     B = x.shape[0]
     y = torch.full((B, n_dst), -7.0, dtype=torch.float64 if ydtype == np.float64 else torch.float32, device="cuda")
     _lib.check(lib.smm_apply(h, level, x.data_ptr(), 0 if x_np.dtype == np.float32 else 1, B, x.shape[1],
-                             y.data_ptr(), 1 if ydtype == np.float64 else 0, n_dst, int(masked), float(amin),
+                             y.data_ptr(), 1 if ydtype == np.float64 else 0, n_dst, int(masked), float(amin), opts,
                              torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     return y.cpu().numpy()
@@ -248,13 +249,13 @@ def test_host_apply_and_strides(smm_lib, oracle, cuda):
         fr = np.ascontiguousarray(w["dst_grid_frac"], np.float64)
         _lib.check(smm_lib.smm_set_dst_mask(h, 0, None, fr.ctypes.data))
         y = np.zeros((B, n_dst), np.float64)
-        _lib.check(smm_lib.smm_apply_host(h, 0, x.ctypes.data, 0, B, n_src, y.ctypes.data, 1, n_dst, 0, 0.5, 16))
+        _lib.check(smm_lib.smm_apply_host(h, 0, x.ctypes.data, 0, B, n_src, y.ctypes.data, 1, n_dst, 0, 0.5, None, 16))
         assert_parity(y, y_ref, RTOL_F64, "host")
         # padded strides on the device path (ldx = n_src + 4 keeps 16-byte rows for TMA)
         xp = torch.zeros((B, n_src + 4), dtype=torch.float32, device="cuda")
         xp[:, :n_src] = torch.from_numpy(x).cuda()
         yp = torch.full((B, n_dst + 3), 5.0, dtype=torch.float64, device="cuda")
-        _lib.check(smm_lib.smm_apply(h, 0, xp.data_ptr(), 0, B, n_src + 4, yp.data_ptr(), 1, n_dst + 3, 0, 0.5, None))
+        _lib.check(smm_lib.smm_apply(h, 0, xp.data_ptr(), 0, B, n_src + 4, yp.data_ptr(), 1, n_dst + 3, 0, 0.5, None, None))
         torch.cuda.synchronize()
         assert_parity(yp[:, :n_dst].cpu().numpy(), y_ref, RTOL_F64, "strided")
         assert (yp[:, n_dst:] == 5.0).all()
@@ -262,7 +263,7 @@ def test_host_apply_and_strides(smm_lib, oracle, cuda):
         xo = torch.zeros((B, n_src + 1), dtype=torch.float32, device="cuda")
         xo[:, :n_src] = torch.from_numpy(x).cuda()
         yo = torch.empty((B, n_dst), dtype=torch.float64, device="cuda")
-        _lib.check(smm_lib.smm_apply(h, 0, xo.data_ptr(), 0, B, n_src + 1, yo.data_ptr(), 1, n_dst, 0, 0.5, None))
+        _lib.check(smm_lib.smm_apply(h, 0, xo.data_ptr(), 0, B, n_src + 1, yo.data_ptr(), 1, n_dst, 0, 0.5, None, None))
         torch.cuda.synchronize()
         assert_parity(yo.cpu().numpy(), y_ref, RTOL_F64, "unaligned")
     finally:
@@ -293,9 +294,9 @@ def test_full_size_properties(smm_lib, cuda):
     x1[7] = float("nan")
     y1n = rg.regrid(x1).reshape(B, n_dst)
     assert torch.isnan(y1n[7]).all() and not torch.isnan(y1n[6]).any()
-    rg.weights_matrix.set_kernel("gather")
+    rg.kernel = "gather"
     yg = rg.regrid(x1).reshape(B, n_dst)
-    rg.weights_matrix.set_kernel(None)
+    rg.kernel = None
     assert torch.equal(torch.isnan(yg), torch.isnan(y1n))
     ok = ~torch.isnan(yg)
     assert torch.allclose(yg[ok], y1n[ok], rtol=1e-12, atol=0)
@@ -391,7 +392,7 @@ def test_c2_full_size_properties(smm_lib, cuda):
     mean_s = (x.double().reshape(B, 721, 1440) * a_s).sum((1, 2)) / a_s.sum()
     mean_d = (y * a_d).sum((1, 2)) / a_d.sum()
     assert torch.allclose(mean_s, mean_d, rtol=1e-11, atol=0)
-    rg.weights_matrix.set_kernel("gather")
+    rg.kernel = "gather"
     yg = rg.regrid(x).reshape(B, 180, 360)
     assert torch.allclose(yg, y, rtol=1e-12, atol=0)
 
@@ -440,7 +441,7 @@ def test_concurrent_applies_on_streams(smm_lib, oracle, cuda):
                 for _ in range(20):
                     yd = torch.empty((B, n_dst), dtype=torch.float64, device="cuda")
                     _lib.check(smm_lib.smm_apply(h, 0, xd.data_ptr(), 0, B, n_src, yd.data_ptr(), 1, n_dst, 0, 0.5,
-                                                 st.cuda_stream))
+                                                 None, st.cuda_stream))
                 st.synchronize()
                 assert_parity(yd.cpu().numpy(), y_ref, RTOL_F64, f"thread {seed}")
         except Exception as e:          # noqa: BLE001
@@ -485,7 +486,7 @@ def test_renormalising_extension(smm_lib, oracle, cuda, xdt):
         ref = oracle.apply_weights_renorm_np(x, mat, imask, w["dst_grid_frac"], 0.5, False, min_valid)
         rg = Regridder(weights=w, remap_area_min=0.5, renormalize=min_valid)
         for kernel in (None, "gather"):
-            rg.weights_matrix.set_kernel(kernel)
+            rg.kernel = kernel
             y = rg.regrid(x).reshape(B, n_dst)
             assert_parity(y, ref, 1e-12, f"renorm {min_valid} {kernel}")
         # fewer NaNs than the reference semantics, and values stay in the data range
@@ -528,13 +529,13 @@ def test_levels_mixed_kernels_and_empty_level(smm_lib, oracle, cuda):
         x = synth.synthetic_field((T, 4, n_src), np.float32, seed=T, nan_mode="random")
         y_ref = oracle.regrid3d_np(x, 1, w.levels, w.levels, mats, imask, v["dst_grid_frac"], masked, 0.0)
         for kernel in (None, "compact"):                   # compact: the scattered level takes the two-pass path
-            rg.weights_matrix.set_kernel(kernel)
+            rg.kernel = kernel
             y = rg.regrid(x).reshape(T, 4, n_dst)
             assert_parity(y, y_ref, RTOL_F64, f"mixed T={T} {kernel}")
             assert np.isnan(y[:, 2]).all()                 # no links -> masked level -> NaN everywhere
     # many time steps, device data with the level stride (the scattered level may go two-pass by itself)
     import torch
-    rg.weights_matrix.set_kernel(None)
+    rg.kernel = None
     x = synth.synthetic_field((40, 4, n_src), np.float32, seed=9, nan_mode="random")
     y_ref = oracle.regrid3d_np(x, 1, w.levels, w.levels, mats, imask, v["dst_grid_frac"], masked, 0.0)
     y = rg.regrid(torch.from_numpy(x).cuda()).cpu().numpy().reshape(40, 4, n_dst)
@@ -614,13 +615,11 @@ def test_packed_rows_threshold_replay_and_renorm(smm_lib, oracle, cuda):
         assert_parity(y, y_ref, RTOL_F64, "packed threshold")
         # renormalising extension on a packed plan
         from smmregrid_b200 import _lib
-        _lib.check(smm_lib.smm_set_renormalize(h, 0.3))
         n0 = smm_lib.smm_launch_count()
-        yr = _apply(smm_lib, h, x, n_dst, np.float64, False, 0.0)
+        yr = _apply(smm_lib, h, x, n_dst, np.float64, False, 0.0, renormalize=0.3)
         assert smm_lib.smm_launch_count() == n0 + 1
         ref = oracle.apply_weights_renorm_np(x, mat, np.ones(n_dst, np.int32), None, 0.0, False, 0.3)
         assert_parity(yr, ref, 1e-12, "packed renorm -> gather")
-        _lib.check(smm_lib.smm_set_renormalize(h, -1.0))
         assert_parity(_apply(smm_lib, h, x, n_dst, np.float64, False, 0.0), y_ref, RTOL_F64, "back to reference mode")
     finally:
         smm_lib.smm_destroy(h)
@@ -753,9 +752,9 @@ def test_c5_full_size_properties(smm_lib, cuda):
     n0 = smm_lib.smm_launch_count()
     y = rg.regrid(x).reshape(B, -1)
     assert smm_lib.smm_launch_count() - n0 == 2                    # two passes, one chunk of <= 64 steps
-    rg.weights_matrix.set_kernel("gather")
+    rg.kernel = "gather"
     yg = rg.regrid(x).reshape(B, -1)
-    rg.weights_matrix.set_kernel(None)
+    rg.kernel = None
     assert torch.allclose(y, yg, rtol=1e-12, atol=0) and not torch.isnan(y).any()
     yc = rg.regrid(torch.full((16, rg.n_src), 3.25, device="cuda", dtype=torch.float64)).reshape(16, -1)
     assert torch.allclose(yc, torch.full_like(yc, 3.25), rtol=1e-13, atol=0)

@@ -56,7 +56,7 @@ def test_random_operator_matches_oracle(smm_lib, oracle, cuda, c):
     y_ref = oracle.apply_weights_c(c["x"], mat, c["imask"], c["frac"], c["amin"], c["masked"])
     h = ctypes.c_void_p()
     _lib.check(smm_lib.smm_create(c["n_src"], c["n_dst"], c["src"].size, c["src"].ctypes.data, c["dst"].ctypes.data,
-                                  c["w"].ctypes.data, 1, 1, 0, ctypes.byref(h)))
+                                  c["w"].ctypes.data, 1, 1, 0, None, ctypes.byref(h)))
     try:
         _lib.check(smm_lib.smm_set_dst_mask(h, 0, c["imask"].ctypes.data, c["frac"].ctypes.data))
         B, n_src, n_dst = c["x"].shape[0], c["n_src"], c["n_dst"]
@@ -67,11 +67,10 @@ def test_random_operator_matches_oracle(smm_lib, oracle, cuda, c):
         with np.errstate(over="ignore"):
             ref = y_ref.astype(c["ydt"])
         for kernel in (0, 2, 3):           # automatic, direct gathers, two-pass compact path for gather-family levels
-            _lib.check(smm_lib.smm_set_kernel(h, kernel))
             y = torch.full((B, n_dst), 3.0, dtype=torch.float64 if c["ydt"] == np.float64 else torch.float32, device="cuda")
             _lib.check(smm_lib.smm_apply(h, 0, xd.data_ptr(), 0 if c["x"].dtype == np.float32 else 1, B, ldx,
                                          y.data_ptr(), 1 if c["ydt"] == np.float64 else 0, n_dst,
-                                         int(c["masked"]), c["amin"], None))
+                                         int(c["masked"]), c["amin"], _lib.apply_opts(kernel), None))
             torch.cuda.synchronize()
             got = y.cpu().numpy()
             assert np.array_equal(np.isnan(got), np.isnan(ref))

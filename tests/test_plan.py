@@ -14,7 +14,7 @@ from helpers import assert_parity, random_links
 
 
 class HostPlan:
-    def __init__(self, lib, src, dst, rm, n_src, n_dst):
+    def __init__(self, lib, src, dst, rm, n_src, n_dst, summation=0, cache_dir=None):
         from smmregrid_b200 import _lib
         self.lib = lib
         src = np.ascontiguousarray(src, np.int32)
@@ -22,7 +22,7 @@ class HostPlan:
         rm = np.ascontiguousarray(rm, np.float64)
         h = ctypes.c_void_p()
         _lib.check(lib.smm_host_plan_build(n_src, n_dst, src.size, src.ctypes.data, dst.ctypes.data,
-                                           rm.ctypes.data, rm.shape[1], 1, ctypes.byref(h)))
+                                           rm.ctypes.data, rm.shape[1], 1, _lib.create_opts(summation, cache_dir), ctypes.byref(h)))
         inf = _lib.SmmInfo()
         ns = ctypes.c_int64()
         _lib.check(lib.smm_host_plan_info(h, ctypes.byref(inf), ctypes.byref(ns)))
@@ -48,6 +48,46 @@ class HostPlan:
             self.rowslot = np.empty((nt, 4, nct), np.int32)
             _lib.check(lib.smm_host_plan_rowslot(h, self.rowslot.ctypes.data))
         lib.smm_host_plan_free(h)
+
+    def emulate_reference_order(self, x):
+        """What the ORD staged kernels compute for filled input x [B, n_src]: one chain per row
+        in (lane, slot) order -- lane l of a row's group holds links l*kpl .. of its ascending-source
+        list -- with separate multiply and add (numpy never contracts to FMA)."""
+        assert self.info["summation"] == 2
+        B = x.shape[0]
+        lpr, kpl = self.info["lanes_per_row"], self.info["links_per_lane"]
+        y = np.zeros((B, self.info["n_dst"]))
+        for t, (row0, nrows, seg0, nseg, elems, *_r) in enumerate(self.tiles):
+            stage = np.zeros((B, max(elems, 1)))
+            for s, d, ln, _p in self.segs[seg0:seg0 + nseg]:
+                stage[:, d:d + ln] = x[:, s:s + ln]
+            prod = stage[:, self.iplan[t]] * self.wplan[t][None]                 # [B, kpl, nct], each rounded once
+            if self.rowslot is not None:
+                rs = self.rowslot[t]
+                chain = np.zeros((B, self.nct))
+                last = np.zeros((B, 4, self.nct))
+                for u in range(4):
+                    chain = np.where(rs[u] == -2, chain, 0.0)                    # a continuation keeps the chain
+                    for j in range(4):
+                        chain = chain + prod[:, 4 * u + j]
+                    last[:, u] = chain
+                val = last.copy()
+                for u in (2, 1, 0):                                              # a row's value = chain after its last sub-row
+                    val[:, u] = np.where(rs[u + 1] == -2, val[:, u + 1], last[:, u])
+                own = rs >= 0
+                assert own.sum() == nrows
+                y[:, rs[own]] = val[:, own]
+                continue
+            rows = np.zeros((B, self.nct // lpr))
+            p4 = prod.reshape(B, kpl, self.nct // lpr, lpr)
+            for l in range(lpr):
+                for k in range(kpl):
+                    rows = rows + p4[:, k, :, l]
+            if self.rowmap is None:
+                y[:, row0:row0 + nrows] = rows[:, :nrows]
+            else:
+                y[:, self.rowmap[row0:row0 + nrows]] = rows[:, :nrows]
+        return y
 
     def emulate(self, x):
         """What staged_kernel computes for filled input x [B, n_src] (float64 math)."""
@@ -176,7 +216,7 @@ def test_address_range_errors(smm_lib):
     for src, dst in (([0], [1]), ([1], [0]), ([11], [1]), ([1], [5])):
         s, d = np.array(src, np.int32), np.array(dst, np.int32)
         w = np.ones((1, 1))
-        rc = smm_lib.smm_host_plan_build(10, 4, 1, s.ctypes.data, d.ctypes.data, w.ctypes.data, 1, 1, ctypes.byref(h))
+        rc = smm_lib.smm_host_plan_build(10, 4, 1, s.ctypes.data, d.ctypes.data, w.ctypes.data, 1, 1, None, ctypes.byref(h))
         assert rc == _lib.SMM_ERR_RANGE
         assert b"outside the grids" in smm_lib.smm_last_error()
 
@@ -276,7 +316,7 @@ def test_compact_plan_of_scattered_operator(smm_lib):
     s32, d32 = np.ascontiguousarray(src, np.int32), np.ascontiguousarray(dst, np.int32)
     h = ctypes.c_void_p()
     _lib.check(smm_lib.smm_host_plan_build(n_src, n_dst, s32.size, s32.ctypes.data, d32.ctypes.data,
-                                           w.ctypes.data, 1, 1, ctypes.byref(h)))
+                                           w.ctypes.data, 1, 1, None, ctypes.byref(h)))
     try:
         inf = _lib.SmmInfo()
         _lib.check(smm_lib.smm_host_plan_info(h, ctypes.byref(inf), None))
@@ -335,3 +375,73 @@ def test_packed_rows_corner_cases(smm_lib, oracle, pattern):
     mat = oracle.compute_weights_matrix_c(src + 1, dst + 1, w, n_src, n_dst)
     x = rng.standard_normal((2, n_src)) + 2
     assert_parity(p.emulate(x), oracle.apply_weights_c(x, mat, None, None, 0.0, False), 1e-12, pattern)
+
+
+@pytest.mark.parametrize("nnz_per_row", [2, 7, 12, 30, 60, 120, 200])
+def test_reference_order_plan_is_bit_identical_to_the_oracle(smm_lib, oracle, nnz_per_row):
+    """Operators with negative weights are planned for reference-order summation (SMM_SUM_AUTO):
+    emulating the ORD kernels' chain over the plan arrays reproduces the oracle BIT FOR BIT,
+    for lane-per-row and packed layouts; a positive operator keeps the fast placement unless
+    SMM_SUM_REFERENCE is asked for."""
+    rng = np.random.default_rng(40 + nnz_per_row)
+    n_src, n_dst, B = 3000, 500, 5
+    counts = rng.integers(0, nnz_per_row + 1, size=n_dst)
+    counts[3] = nnz_per_row
+    dst = np.repeat(np.arange(n_dst), counts)
+    src = np.clip((dst * n_src) // n_dst + rng.integers(-200, 200, size=dst.size), 0, n_src - 1)
+    w = rng.standard_normal(dst.size)                      # both signs: sums cancel
+    o = np.lexsort((src, dst))
+    src, dst, w = (src[o] + 1).astype(np.int32), (dst[o] + 1).astype(np.int32), w[o].reshape(-1, 1)
+    x = rng.standard_normal((B, n_src)) * 50
+    plan = HostPlan(smm_lib, src, dst, w, n_src, n_dst)
+    assert plan.info["summation"] == 2 and plan.info["kernel_name"] == "staged"
+    assert plan.info["consumer_threads"] == 256
+    mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False)
+    y = plan.emulate_reference_order(x)
+    assert np.array_equal(y, y_ref), float(np.abs(y - y_ref).max())
+    # the same operator forced to the fast placement, and a positive one forced to reference order
+    assert HostPlan(smm_lib, src, dst, w, n_src, n_dst, summation=1).info["summation"] == 1
+    wp = np.abs(w)
+    assert HostPlan(smm_lib, src, dst, wp, n_src, n_dst).info["summation"] == 1
+    planp = HostPlan(smm_lib, src, dst, wp, n_src, n_dst, summation=2)
+    matp = oracle.compute_weights_matrix_c(src, dst, wp, n_src, n_dst)
+    assert np.array_equal(planp.emulate_reference_order(x), oracle.apply_weights_c(x, matp, None, None, 0.0, False))
+
+
+def test_plan_cache_round_trip(smm_lib, tmp_path):
+    """On-disk cache of the operator construction: a second build of the same links is a hit and
+    returns byte-identical CSR + plan arrays; different links, a different summation order, a
+    truncated or foreign file are misses that rebuild (and repair) silently."""
+    import os
+    from smmregrid_b200 import synth
+    w = synth.config_weights("C4", 10)
+    n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+    args = (smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    d = str(tmp_path / "plans")
+    a = HostPlan(*args, cache_dir=d)
+    assert a.info["plan_cache_hit"] == 0
+    files = os.listdir(d)
+    assert len(files) == 1 and files[0].endswith(".plan")
+    b = HostPlan(*args, cache_dir=d)
+    assert b.info["plan_cache_hit"] == 1
+    for name in ("rowptr", "col", "val", "tiles", "segs", "wplan", "iplan"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    assert {k: v for k, v in a.info.items() if k != "plan_cache_hit"} == \
+        {k: v for k, v in b.info.items() if k != "plan_cache_hit"}
+    # other summation order -> other key; other weights -> other key
+    assert HostPlan(*args, summation=2, cache_dir=d).info["plan_cache_hit"] == 0
+    rm2 = np.array(w["remap_matrix"]); rm2[0, 0] *= 0.5
+    assert HostPlan(smm_lib, w["src_address"], w["dst_address"], rm2, n_src, n_dst, cache_dir=d).info["plan_cache_hit"] == 0
+    assert len(os.listdir(d)) == 3
+    # a damaged file is a miss and is rewritten
+    path = os.path.join(d, files[0])
+    size = os.path.getsize(path)
+    with open(path, "r+b") as f:
+        f.truncate(size // 2)
+    c = HostPlan(*args, cache_dir=d)
+    assert c.info["plan_cache_hit"] == 0 and np.array_equal(c.wplan, a.wplan)
+    assert os.path.getsize(path) == size
+    assert HostPlan(*args, cache_dir=d).info["plan_cache_hit"] == 1
+    # an unwritable directory only disables the cache
+    assert HostPlan(*args, cache_dir="/proc/definitely/not/writable").info["plan_cache_hit"] == 0
