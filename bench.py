@@ -19,6 +19,7 @@ bounded sample.  `--impl reference` times that CPU port as its own arm.
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -42,7 +43,11 @@ def parse():
     ap.add_argument("--workload", default="C4", help="C4 (default) | C2 | C4s<k> (C4 grids scaled down k x)")
     ap.add_argument("--batch", type=int, default=0, help="resident batch rows per GPU (0 = workload default)")
     ap.add_argument("--e2e-batch", type=int, default=128, help="host batch rows per e2e step")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--strong-rows", type=int, default=8760,
+                    help="fixed total batch rows of the strong-scaling sub-record (the north-star year); 0 = skip")
+    ap.add_argument("--strong-steps", type=int, default=3)
+    ap.add_argument("--no-others", action="store_true", help="skip the other_configs records (N = 1 only)")
     ap.add_argument("--xdtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--ydtype", default="f64", choices=["f32", "f64"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -77,6 +82,35 @@ def workload(name):
         (ls, ts), (ld, td) = [tuple(int(v) for v in g.split("x")) for g in (a, b)]
         return synth.bilinear_latlon(ls, ts, ld, td), 256, f"remapbil {ls}x{ts} -> {ld}x{td}"
     raise SystemExit(f"unknown workload {name}")
+
+
+def kernel_source_hash():
+    """sha1 over the kernel sources: ties an ncu capture (profiles/traffic.json) to the code it
+    was taken from (the GPU box has no .git)."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "smmregrid_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h", ".cpp")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(workload_name, batch_rows, xdtype, ydtype):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu capture of this exact
+    configuration, or None -- also None when the capture predates the current kernel sources
+    (scripts/round_evidence.sh regenerates profiles/traffic.json and records the hash)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if t.get("kernel_source_hash") != kernel_source_hash():
+            return None
+        for c in t["captures"]:
+            if (c["workload"], c["batch_rows"], c["x_dtype"], c["y_dtype"]) == (workload_name, batch_rows, xdtype, ydtype):
+                return c["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    return None
 
 
 def algorithmic_bytes(info, B, sx, sy, masked, area_min):
@@ -197,8 +231,6 @@ def run_3d(args, rg, w, T, xdt, ydt, sx, sy, area_min, dev, g, world, rank, desc
     import torch
     from smmregrid_b200 import _lib
     L, n_src, n_dst = rg.weights_matrix.n_levels, rg.n_src, rg.n_dst
-    if args.kernel != "auto":
-        rg.weights_matrix.set_kernel(args.kernel)
     x = torch.empty((T, L, n_src), dtype=xdt, device=dev)
     x.normal_(10.0, 2.0, generator=g)
     land = torch.from_numpy(np.asarray(w["src_grid_imask"]).reshape(L, n_src) == 0).to(dev)
@@ -221,13 +253,7 @@ def run_3d(args, rg, w, T, xdt, ydt, sx, sy, area_min, dev, g, world, rank, desc
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = abytes / (ms * 1e-3) / 1e9
-    traffic = None            # per launch, from the committed ncu capture of this configuration
-    try:
-        for t in json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["captures"]:
-            if (t["workload"], t["batch_rows"], t["x_dtype"], t["y_dtype"]) == (args.workload, T, args.xdtype, args.ydtype):
-                traffic = t["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    traffic = measured_traffic(args.workload, T, args.xdtype, args.ydtype)
     print(json.dumps({
         "metric": METRIC, "value": T * L * n_src / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -238,6 +264,70 @@ def run_3d(args, rg, w, T, xdt, ydt, sx, sy, area_min, dev, g, world, rank, desc
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": abytes},
         "gpu_launches": int(lib.smm_launch_count() - l0)}), flush=True)
+
+
+def other_configs(dev, peak):
+    """The other BASELINE configurations on the same box, a few launches each (device-resident
+    slab, CUDA events): ms, GB/s and fraction of the measured peak for both byte models."""
+    import numpy as np
+    import torch
+    from smmregrid_b200 import Regridder, _lib, synth
+    lib = _lib.load()
+    out = []
+    specs = [("C2", "C2", 1024, "none"), ("C2 + static land mask (35 % of sources NaN)", "C2", 1024, "land"),
+             ("C3", "C3", 48, "levels"), ("C5nn", "C5nn", 64, "none"), ("C5dis", "C5dis", 64, "none")]
+    for label, name, B, nan in specs:
+        t_build = time.perf_counter()
+        w, _, desc = workload(name)
+        rg = Regridder(weights=w, remap_area_min=0.5, device=dev.index)
+        t_build = time.perf_counter() - t_build
+        L = rg.weights_matrix.n_levels
+        infos = [rg.weights_matrix.info(l) for l in range(L)]
+        n_src, n_dst = rg.n_src, rg.n_dst
+        g = torch.Generator(device=dev).manual_seed(77)
+        shape = (B, L, n_src) if rg.mask_dim else (B, n_src)
+        x = torch.empty(shape, dtype=torch.float32, device=dev)
+        x.normal_(280.0, 20.0, generator=g)
+        if nan == "land":
+            ii = torch.arange(n_src, device=dev, dtype=torch.float32)
+            nlon = float(np.atleast_1d(w["src_grid_dims"])[0])
+            lon, lat = (ii % nlon) / nlon * 6.2832, torch.floor(ii / nlon) / (n_src / nlon) * 3.1416
+            x[:, (torch.sin(2 * lon + 0.5) * torch.sin(lat) + 0.6 * torch.cos(3 * lon - 1.0) * torch.sin(2 * lat)) > 0.25] = float("nan")
+        elif nan == "levels":
+            x[:, torch.from_numpy(np.asarray(w["src_grid_imask"]).reshape(L, n_src) == 0).to(dev)] = float("nan")
+        for _ in range(3):
+            y = rg.regrid(x)
+        torch.cuda.synchronize(dev)
+        l0 = lib.smm_launch_count()
+        steps = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            y = rg.regrid(x)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        launches = (lib.smm_launch_count() - l0) // steps
+        nnz = sum(i["nnz"] for i in infos)
+        masked = bool(np.any(rg.masked))
+        fixed = nnz * 12 + L * ((n_dst + 1) * 4 + n_dst * 8 + (n_dst if masked else 0))
+        touched = sum(i["touched_src"] for i in infos)
+        ab = fixed + B * L * (n_src * 4 + n_dst * 8)
+        ab_t = fixed + B * (touched * 4 + L * n_dst * 8)
+        kern = infos[0]["kernel_name"]
+        if kern == "gather" and launches >= 2:
+            kern = "compact_kernel + compact_apply_kernel"
+        out.append({"config": label, "workload": desc, "batch_rows": B, "levels": L, "x_dtype": "f32", "y_dtype": "f64",
+                    "ms_per_launch_group": ms, "launches_per_apply": int(launches), "kernel": kern,
+                    "packed_rows": infos[0]["packed_rows"], "lanes_per_row": infos[0]["lanes_per_row"],
+                    "summation": infos[0]["summation_name"],
+                    "achieved_gbs": ab / (ms * 1e-3) / 1e9, "frac": ab / (ms * 1e-3) / 1e9 / peak,
+                    "achieved_touched_src_gbs": ab_t / (ms * 1e-3) / 1e9, "frac_touched_src": ab_t / (ms * 1e-3) / 1e9 / peak,
+                    "src_points_per_s": B * L * n_src / (ms * 1e-3), "operator_build_s": round(t_build, 2),
+                    "nan_cells_out": int(torch.isnan(y).sum().item())})
+        del x, y, rg, w
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -273,9 +363,8 @@ def main():
     ydt = np.float32 if args.ydtype == "f32" else np.float64
     sx, sy = (4 if args.xdtype == "f32" else 8), (4 if args.ydtype == "f32" else 8)
     area_min = 0.5
-    rg = Regridder(weights=w, remap_area_min=area_min, device=local, out_dtype=ydt)
-    if args.kernel != "auto":
-        rg.weights_matrix.set_kernel(args.kernel)
+    rg = Regridder(weights=w, remap_area_min=area_min, device=local, out_dtype=ydt,
+                   kernel=None if args.kernel == "auto" else args.kernel)
     info = rg.weights_matrix.info()
     n_src, n_dst = rg.n_src, rg.n_dst
     masked = bool(np.any(rg.masked))
@@ -307,9 +396,11 @@ def main():
     stream = torch.cuda.current_stream(dev)
     xcode, ycode = (0 if args.xdtype == "f32" else 1), (0 if args.ydtype == "f32" else 1)
 
+    opts = _lib.apply_opts(rg.kernel)
+
     def step():
         _lib.check(lib.smm_apply(rg.weights_matrix.handle, 0, x.data_ptr(), xcode, B, n_src,
-                                 y.data_ptr(), ycode, n_dst, int(masked), area_min, stream.cuda_stream))
+                                 y.data_ptr(), ycode, n_dst, int(masked), area_min, opts, stream.cuda_stream))
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -339,31 +430,119 @@ def main():
     total_ms_max = float(tt.item())
     clocks = sampler.stop(t0, t1) if rank == 0 else None
 
-    # ---- e2e: public API from pinned host memory, H2D + D2H inside the timed region
+    # ---- e2e: public API from HOST memory, H2D + D2H inside the timed region
+    def all_max(v):
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed_regrids(xin, steps):
+        """`steps` calls of Regridder.regrid(host array), all ranks at once; max-over-ranks seconds."""
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0e = time.perf_counter()
+        for _ in range(steps):
+            yh = rg.regrid(xin)
+        torch.cuda.synchronize(dev)
+        dt = all_max(time.perf_counter() - t0e)
+        assert tuple(yh.shape[:1]) == (xin.shape[0],)
+        return dt
+
     e2e = None
     if not args.no_e2e:
         Be = min(args.e2e_batch, B)
+        h2d_bytes, d2h_bytes = Be * n_src * sx, Be * n_dst * sy
         xh = torch.empty((Be, n_src), dtype=xdt, pin_memory=True)
         xh.copy_(x[:Be])
         rg.regrid(xh[: min(Be, 8)])                               # warm the staging buffers
         for _ in range(3):                                        # and torch's pinned-host allocator cache
-            yh = rg.regrid(xh)
-        torch.cuda.synchronize(dev)
+            rg.regrid(xh)
+        te = timed_regrids(xh, args.e2e_steps)
+        e2e_val = world * Be * n_src * args.e2e_steps / te
+        # what the PCIe links themselves sustain: bare cudaMemcpyAsync of the same pinned bytes,
+        # all ranks at the same time (and the result's bytes in the other direction)
+        sec = ctypes.c_double()
         if world > 1:
             dist.barrier()
-        te0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            yh = rg.regrid(xh)
-        torch.cuda.synchronize(dev)
-        te = torch.tensor([time.perf_counter() - te0], dtype=torch.float64, device=dev)
+        _lib.check(lib.smm_copy_ceiling(local, xh.data_ptr(), h2d_bytes, 0, 5, ctypes.byref(sec)))
+        h2d_s = all_max(sec.value)
+        yh_pin = torch.empty((Be, n_dst), dtype=y.dtype, pin_memory=True)
         if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_val = world * Be * n_src * args.e2e_steps / float(te.item())
-        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": Be * n_src * sx,
-               "d2h_bytes_per_step": Be * n_dst * sy, "batch_rows_per_step": Be,
-               "ms_per_step": 1e3 * float(te.item()) / args.e2e_steps,
-               "api": "Regridder.regrid(pinned host tensor) -> smm_apply_host", "numa_node": numa}
-        assert tuple(yh.shape[:1]) == (Be,)
+            dist.barrier()
+        _lib.check(lib.smm_copy_ceiling(local, yh_pin.data_ptr(), d2h_bytes, 1, 5, ctypes.byref(sec)))
+        d2h_s = all_max(sec.value)
+        ceiling_gbs = world * h2d_bytes / h2d_s / 1e9
+        e2e_h2d_gbs = world * h2d_bytes * args.e2e_steps / te / 1e9
+        # second figure: PAGEABLE numpy input, what Regridder.regrid(DataArray / ndarray) is handed
+        # in practice (goes through pinned bounce buffers filled by host threads)
+        xp = xh.numpy().copy()
+        rg.regrid(xp)
+        p_steps = max(3, args.e2e_steps // 2)
+        tp = timed_regrids(xp, p_steps)
+        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": d2h_bytes, "batch_rows_per_step": Be, "steps": args.e2e_steps,
+               "ms_per_step": 1e3 * te / args.e2e_steps,
+               "api": "Regridder.regrid(pinned host tensor) -> smm_apply_host", "numa_node": numa,
+               "h2d_gbs": e2e_h2d_gbs,
+               "h2d_ceiling_gbs": ceiling_gbs,
+               "d2h_ceiling_gbs": world * d2h_bytes / d2h_s / 1e9,
+               "frac_of_ceiling": e2e_h2d_gbs / ceiling_gbs,
+               "ceiling": f"bare pinned cudaMemcpyAsync of the same bytes, 5 back-to-back copies, all {world} rank(s) concurrently, max over ranks",
+               "pageable": {"value": world * Be * n_src * p_steps / tp, "unit": UNIT, "steps": p_steps,
+                            "ms_per_step": 1e3 * tp / p_steps, "h2d_gbs": world * h2d_bytes * p_steps / tp / 1e9,
+                            "api": "Regridder.regrid(pageable numpy array): pinned bounce buffers filled by host threads"}}
+        del xp, yh_pin
+
+    # ---- strong scaling: the fixed north-star job (8760 steps) over the ranks of this run, with
+    # the final host gather over NCCL inside the timed region
+    strong = None
+    if args.strong_rows > 0 and not is3d:
+        from smmregrid_b200.shard import batch_shard, gather_to_host
+        Bs = args.strong_rows
+        r0, r1 = batch_shard(Bs, world, rank)
+        rows = r1 - r0
+        y_full = torch.empty((rows, n_dst), dtype=y.dtype, device=dev)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def strong_step():
+            """this rank's block of the year in resident chunks of <= B rows, then the gather"""
+            ev0.record(stream)
+            for c0 in range(0, rows, B):
+                nb = min(B, rows - c0)
+                _lib.check(lib.smm_apply(rg.weights_matrix.handle, 0, x.data_ptr(), xcode, nb, n_src,
+                                         y_full[c0:].data_ptr(), ycode, n_dst, int(masked), area_min, opts,
+                                         stream.cuda_stream))
+            ev1.record(stream)
+            return gather_to_host(y_full, Bs, dst=0)
+
+        full = strong_step()                                      # warm-up (NCCL channels, pinned result buffer)
+        if rank == 0:
+            assert tuple(full.shape) == (Bs, n_dst)
+        apply_ms, total_s = [], []
+        for _ in range(args.strong_steps):
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            ts0 = time.perf_counter()
+            full = strong_step()
+            torch.cuda.synchronize(dev)
+            total_s.append(all_max(time.perf_counter() - ts0))
+            apply_ms.append(all_max(ev0.elapsed_time(ev1)))
+        tot = sum(total_s) / len(total_s)
+        app = 1e-3 * sum(apply_ms) / len(apply_ms)
+        strong = {"scaling": "strong", "total_batch_rows": Bs, "rows_per_rank": -(-Bs // world),
+                  "value": Bs * n_src / tot, "unit": UNIT, "ms_per_step": 1e3 * tot, "steps": args.strong_steps,
+                  "apply_ms": 1e3 * app, "gather_ms": 1e3 * (tot - app), "gather_frac": (tot - app) / tot,
+                  "gather_bytes": Bs * n_dst * sy,
+                  "gather": ("shard.gather_to_host: NCCL gather of the ranks' [rows, n_dst] blocks to rank 0 + "
+                             "device->host copy into one pinned [8760, n_dst] array" if world > 1
+                             else "device->host copy of the [8760, n_dst] result"),
+                  "data": "every resident chunk re-reads the rank's synthetic %d-row slab (%.1f GB >> L2); "
+                          "results go to distinct rows" % (B, B * n_src * sx / 1e9),
+                  "value_apply_only": Bs * n_src / app}
+        del y_full, full
 
     if rank != 0:
         if world > 1:
@@ -379,13 +558,7 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
     abytes = algorithmic_bytes(info, B, sx, sy, masked, area_min)
-    traffic = None            # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
-    try:
-        for t in json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["captures"]:
-            if (t["workload"], t["batch_rows"], t["x_dtype"], t["y_dtype"]) == (args.workload, B, args.xdtype, args.ydtype):
-                traffic = t["dram_bytes_per_launch"]
-    except Exception:
-        pass
+    traffic = measured_traffic(args.workload, B, args.xdtype, args.ydtype)
     avg_launch_s = 1e-3 * sum(per_launch_ms) / len(per_launch_ms)
     achieved = abytes / avg_launch_s / 1e9
     value = world * B * n_src * args.steps / (total_ms_max * 1e-3)
@@ -397,6 +570,12 @@ def main():
         tput, times = cpu_port_throughput(w, cores, rows, 3)
         cpu = {"value": tput, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{rows} batch rows of the same workload, best of 3 ({min(times) * 1e3:.0f} ms)"}
+
+    others = None
+    if world == 1 and not args.no_others and args.workload == "C4":
+        del x, y
+        torch.cuda.empty_cache()
+        others = other_configs(dev, peak)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -411,6 +590,8 @@ def main():
                    "l2": "resident slab (%.1f GB) >> 126 MB L2, no flush" % (B * n_src * sx / 1e9)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "traffic_source": ("profiles/traffic.json (ncu --set full of this configuration, kernel sources %s)" % kernel_source_hash())
+                     if traffic is not None else "no ncu capture of the current kernel sources",
                      "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": avg_launch_s * 1e3,
                      "kernel": "smm::staged_kernel" if info["kernel_name"] == "staged"
                      else ("smm::gather_kernel" if launches <= args.steps
@@ -423,6 +604,10 @@ def main():
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if strong is not None:
+        line["strong"] = strong
+    if others is not None:
+        line["other_configs"] = others
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)

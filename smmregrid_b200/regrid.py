@@ -500,9 +500,10 @@ class Regridder(object):
         kept_shape = tuple(sizes[d] for d in kept_canon)
         out_dt = self._out_np_dtype()
 
-        data = da.data
-        if _is_dask(data):
-            values = self._dask_apply(data, len(horizontal), levels, out_dt)
+        # `.chunks` is None unless the variable is dask-backed; `.data` of a lazily indexed backend
+        # array would load the whole field, so it is only touched for dask
+        if getattr(da, "chunks", None):
+            values = self._dask_apply(da.data, len(horizontal), levels, out_dt)
         else:
             values = self._stream_blocks(da, other, lev_dim, levels, kept_shape, out_dt)
         out_dims = kept_canon

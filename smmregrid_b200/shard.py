@@ -26,27 +26,51 @@ def shard_sizes(B: int, world: int):
 
 
 def gather_to_host(y_local, B: int, group=None, dst: Optional[int] = 0):
-    """Assemble the full ``[B, ...]`` result from per-rank blocks (order = rank order).
+    """Assemble the full ``[B, ...]`` result from per-rank blocks (order = rank order) -- the one
+    collective of the path, after the hot loop ("the final host gather").
 
     ``y_local``: this rank's ``[b_rank, ...]`` torch tensor (CUDA with NCCL, CPU with gloo).
-    Returns a CPU tensor on rank ``dst`` (all ranks if ``dst is None``), else ``None``.
-    Blocks are padded to ``ceil(B / world)`` rows for ``all_gather_into_tensor``.
+    Returns a CPU tensor on rank ``dst`` (pinned when the blocks are CUDA tensors), else ``None``;
+    ``dst=None`` returns it on every rank.  With a destination rank the blocks travel once
+    (``gather``: the device of rank ``dst`` receives the other ranks' blocks over NVLink and
+    every block is copied device->host straight into its rows of the result); ``dst=None`` uses
+    ``all_gather_into_tensor``.  Blocks shorter than ``ceil(B / world)`` rows (the last ranks)
+    are padded for the collective only.
     """
     import torch
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()):
-        return y_local.cpu()
+        if not y_local.is_cuda:
+            return y_local
+        host = torch.empty(tuple(y_local.shape), dtype=y_local.dtype, pin_memory=True)
+        host.copy_(y_local, non_blocking=True)
+        torch.cuda.current_stream(y_local.device).synchronize()
+        return host
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     per = -(-B // world)
     tail = tuple(y_local.shape[1:])
-    pad = torch.zeros((per,) + tail, dtype=y_local.dtype, device=y_local.device)
-    pad[: y_local.shape[0]] = y_local
-    out = torch.empty((world * per,) + tail, dtype=y_local.dtype, device=y_local.device)
-    dist.all_gather_into_tensor(out, pad, group=group)
-    if dst is not None and rank != dst:
+    block = y_local.contiguous()
+    if block.shape[0] != per:
+        block = torch.zeros((per,) + tail, dtype=y_local.dtype, device=y_local.device)
+        block[: y_local.shape[0]] = y_local
+    if dst is None:
+        out = torch.empty((world * per,) + tail, dtype=y_local.dtype, device=y_local.device)
+        dist.all_gather_into_tensor(out, block, group=group)
+        return out[:B].cpu()
+    if rank != dst:
+        dist.gather(block, gather_list=None, dst=dst, group=group)
         return None
-    return out[:B].cpu()
+    bufs = [block if r == rank else torch.empty_like(block) for r in range(world)]
+    dist.gather(block, gather_list=bufs, dst=dst, group=group)
+    host = torch.empty((B,) + tail, dtype=y_local.dtype, pin_memory=y_local.is_cuda)
+    for r in range(world):
+        a, b = batch_shard(B, world, r)
+        if b > a:
+            host[a:b].copy_(bufs[r][: b - a], non_blocking=True)
+    if y_local.is_cuda:
+        torch.cuda.current_stream(y_local.device).synchronize()
+    return host
 
 
 def regrid_sharded(regridder, x, group=None, gather: bool = True, dst: Optional[int] = 0):

@@ -112,6 +112,8 @@ class DataArray:
     def size(self): return self.data.size
     @property
     def sizes(self): return dict(zip(self.dims, self.data.shape))
+    @property
+    def chunks(self): return getattr(self.data, "chunks", None)      # None unless dask-backed, like xarray
     def __array__(self, dtype=None, copy=None): return np.asarray(self.data, dtype=dtype)
     def __len__(self): return len(self.data)
     def _new(self, data, dims=None): return DataArray(data, self.dims if dims is None else dims, name=self.name, attrs=self.attrs)
@@ -203,6 +205,8 @@ class Dataset:
     def __setitem__(self, k, v):
         if isinstance(v, tuple):
             v = DataArray(v[1], v[0], name=k)
+        if v.name is None:
+            v.name = k
         self.variables[k] = v
 
     def __getitem__(self, k): return self.variables[k]

@@ -704,10 +704,10 @@ def test_compact_two_pass_path(smm_lib, oracle, cuda, xdt, ydt, B):
         else:
             assert_parity(y, y_ref.astype(np.float32), RTOL_F32, "compact f32 out")
         # automatic choice (direct gathers here: few links per source column).  The weights of this
-        # case change sign, so sums cancel and an order-changing kernel is only accurate relative
-        # to the magnitude of the terms, not of the result: looser relative tolerance
+        # case change sign, so the operator is summed in the reference's order on every path
+        assert _info(smm_lib, h)["summation_name"] == "reference"
         y_auto = _apply(smm_lib, h, x, n_dst, ydt, True, 0.5, imask, frac, kernel=0)
-        assert_parity(y_auto, y_ref.astype(ydt), 1e-9 if ydt == np.float64 else 1e-5, "auto")
+        assert_parity(y_auto, y_ref.astype(ydt), RTOL_F64 if ydt == np.float64 else RTOL_F32, "auto")
     finally:
         smm_lib.smm_destroy(h)
 
