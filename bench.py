@@ -499,14 +499,18 @@ def main():
     # the final host gather over NCCL inside the timed region
     strong = None
     if args.strong_rows > 0 and not is3d:
-        from smmregrid_b200.shard import batch_shard, gather_to_host
+        from smmregrid_b200.shard import HostGather, batch_shard, gather_to_host
         Bs = args.strong_rows
         r0, r1 = batch_shard(Bs, world, rank)
         rows = r1 - r0
         y_full = torch.empty((rows, n_dst), dtype=y.dtype, device=dev)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # destinations of the gather, allocated once like an application would: a pinned array on
+        # rank 0 (NCCL route) and a shared-memory array every rank maps (direct route)
+        host_pin = torch.empty((Bs, n_dst), dtype=y.dtype, pin_memory=True) if rank == 0 else None
+        hg = HostGather(Bs, (n_dst,), y.dtype, dst=0)
 
-        def strong_step():
+        def strong_step(via):
             """this rank's block of the year in resident chunks of <= B rows, then the gather"""
             ev0.record(stream)
             for c0 in range(0, rows, B):
@@ -515,34 +519,46 @@ def main():
                                          y_full[c0:].data_ptr(), ycode, n_dst, int(masked), area_min, opts,
                                          stream.cuda_stream))
             ev1.record(stream)
-            return gather_to_host(y_full, Bs, dst=0)
+            return gather_to_host(y_full, Bs, dst=0, via=via, out=hg if via == "shm" else host_pin)
 
-        full = strong_step()                                      # warm-up (NCCL channels, pinned result buffer)
-        if rank == 0:
-            assert tuple(full.shape) == (Bs, n_dst)
-        apply_ms, total_s = [], []
-        for _ in range(args.strong_steps):
-            torch.cuda.synchronize(dev)
-            if world > 1:
-                dist.barrier()
-            ts0 = time.perf_counter()
-            full = strong_step()
-            torch.cuda.synchronize(dev)
-            total_s.append(all_max(time.perf_counter() - ts0))
-            apply_ms.append(all_max(ev0.elapsed_time(ev1)))
-        tot = sum(total_s) / len(total_s)
-        app = 1e-3 * sum(apply_ms) / len(apply_ms)
+        def strong_run(via):
+            full = strong_step(via)                               # warm-up (NCCL channels, page faults of the result)
+            if rank == 0:
+                assert tuple(full.shape) == (Bs, n_dst)
+            apply_ms, total_s = [], []
+            for _ in range(args.strong_steps):
+                torch.cuda.synchronize(dev)
+                if world > 1:
+                    dist.barrier()
+                ts0 = time.perf_counter()
+                full = strong_step(via)
+                torch.cuda.synchronize(dev)
+                total_s.append(all_max(time.perf_counter() - ts0))
+                apply_ms.append(all_max(ev0.elapsed_time(ev1)))
+            if rank == 0 and via == "shm":                        # the two routes deliver the same array ...
+                assert torch.equal(full[:: max(1, Bs // 64)].nan_to_num(), host_pin[:: max(1, Bs // 64)].nan_to_num())
+                assert torch.equal(full[:3].nan_to_num(), y_full[:3].cpu().nan_to_num())     # ... which starts with rank 0's rows
+            return sum(total_s) / len(total_s), 1e-3 * sum(apply_ms) / len(apply_ms)
+
+        tot_n, app_n = strong_run("nccl")
+        tot, app = strong_run("shm")
         strong = {"scaling": "strong", "total_batch_rows": Bs, "rows_per_rank": -(-Bs // world),
                   "value": Bs * n_src / tot, "unit": UNIT, "ms_per_step": 1e3 * tot, "steps": args.strong_steps,
                   "apply_ms": 1e3 * app, "gather_ms": 1e3 * (tot - app), "gather_frac": (tot - app) / tot,
                   "gather_bytes": Bs * n_dst * sy,
-                  "gather": ("shard.gather_to_host: NCCL gather of the ranks' [rows, n_dst] blocks to rank 0 + "
-                             "device->host copy into one pinned [8760, n_dst] array" if world > 1
-                             else "device->host copy of the [8760, n_dst] result"),
+                  "gather": "shard.gather_to_host(via='shm'): every rank copies its [rows, n_dst] block device->host "
+                            "over its own PCIe link into its rows of one shared-memory [%d, n_dst] array "
+                            "(registered with the driver once), then a barrier" % Bs,
+                  "nccl_route": {"ms_per_step": 1e3 * tot_n, "apply_ms": 1e3 * app_n, "gather_ms": 1e3 * (tot_n - app_n),
+                                 "value": Bs * n_src / tot_n,
+                                 "gather": ("shard.gather_to_host(via='nccl'): NCCL gather of the ranks' blocks to rank 0 over "
+                                            "NVLink + device->host copy into one pinned array (the whole result crosses ONE PCIe link)")
+                                 if world > 1 else "device->host copy of the result into one pinned array"},
                   "data": "every resident chunk re-reads the rank's synthetic %d-row slab (%.1f GB >> L2); "
                           "results go to distinct rows" % (B, B * n_src * sx / 1e9),
                   "value_apply_only": Bs * n_src / app}
-        del y_full, full
+        hg.close()
+        del y_full, host_pin
 
     if rank != 0:
         if world > 1:

@@ -73,7 +73,8 @@ struct smm_handle {
     mutable cudaMemPool_t pool = nullptr;
     std::mutex host_mu;
     HostSlot slots[kHostSlots];
-    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;     // host pipeline: H2D | applies | D2H
+    cudaStream_t s_in[2] = {nullptr, nullptr};                       // host pipeline: H2D (alternating) ...
+    cudaStream_t s_k = nullptr, s_out = nullptr;                     // ... applies | D2H
 };
 
 namespace {
@@ -655,10 +656,11 @@ namespace {
 // result; `launch(dx, dy, nb, stream)` applies the operator to nb batch rows held contiguously
 // on the device.
 //
-// Three streams, one per engine: ALL host->device copies go back to back on `s_in` (the PCIe
-// link is the bottleneck of the whole pipeline: it must never wait for a kernel or a
-// device->host copy), the applies run on `s_k`, the (50x smaller) results return on `s_out`;
-// events order the three per chunk, and a ring of kHostSlots device buffers lets the copy of
+// Streams per engine: the host->device copies alternate between two streams `s_in[0/1]` (the
+// PCIe link is the bottleneck of the whole pipeline: it must never wait for a kernel or a
+// device->host copy, and with two copies in flight the set-up latency of one hides behind the
+// transfer of the other), the applies run on `s_k`, the (50x smaller) results return on `s_out`;
+// events order them per chunk, and a ring of kHostSlots device buffers lets the copy of
 // chunk i+1.. proceed while chunk i is applied.  Pinned (or registered) host arrays are DMA'd
 // directly.  Pageable arrays -- what numpy / xarray hand over -- go through pinned bounce buffers
 // filled by a few host threads, which overlaps the host copy of chunk i+1 with the PCIe
@@ -681,9 +683,11 @@ int host_pipeline(smm_handle *h, const void *x, size_t row_x, size_t x_stride, v
     DeviceGuard g(h->device);
     const size_t need_x = static_cast<size_t>(chunk_rows) * row_x;
     const size_t need_y = static_cast<size_t>(chunk_rows) * row_y;
-    const int nslots = static_cast<int>(std::min<int64_t>(kHostSlots, (B + chunk_rows - 1) / chunk_rows));
-    for (cudaStream_t *sp : {&h->s_in, &h->s_k, &h->s_out})
+    for (cudaStream_t *sp : {&h->s_in[0], &h->s_in[1], &h->s_k, &h->s_out})
         if (!*sp) CUDA_TRY(cudaStreamCreateWithFlags(sp, cudaStreamNonBlocking));
+    static const int k_in_streams = std::max(1, std::min(2, env_int("SMM_HOST_IN_STREAMS", 2)));
+    static const int k_slots = std::max(2, std::min(kHostSlots, env_int("SMM_HOST_SLOTS", kHostSlots)));
+    const int nslots = static_cast<int>(std::min<int64_t>(k_slots, (B + chunk_rows - 1) / chunk_rows));
     for (int s = 0; s < nslots; ++s) {
         HostSlot &sl = h->slots[s];
         for (cudaEvent_t *ev : {&sl.ev_in, &sl.ev_k, &sl.ev_out})
@@ -726,26 +730,28 @@ int host_pipeline(smm_handle *h, const void *x, size_t row_x, size_t x_stride, v
     // common drain of the streams: queued copies must not outlive the call)
     auto run = [&]() -> int {
         int rc, slot = 0;
-        for (int64_t b0 = 0; b0 < B; b0 += chunk_rows, slot = (slot + 1) % nslots) {
+        int64_t ichunk = 0;
+        for (int64_t b0 = 0; b0 < B; b0 += chunk_rows, slot = (slot + 1) % nslots, ++ichunk) {
             const int64_t nb = std::min(chunk_rows, B - b0);
             HostSlot &sl = h->slots[slot];
+            cudaStream_t s_in = h->s_in[ichunk % k_in_streams];
             const char *xs = static_cast<const char *>(x) + static_cast<size_t>(b0) * x_stride;
             char *ys = static_cast<char *>(y) + static_cast<size_t>(b0) * y_stride;
             const bool reused = pending[slot].used;
             // the result bounce buffer (or nothing) of this slot's previous chunk goes out first
             if (!y_pinned && (rc = drain(slot))) return rc;
-            if (reused) CUDA_TRY(cudaStreamWaitEvent(h->s_in, sl.ev_k, 0));      // dx free: its kernel is done
+            if (reused) CUDA_TRY(cudaStreamWaitEvent(s_in, sl.ev_k, 0));         // dx free: its kernel is done
             if (x_pinned) {
                 if (x_stride == row_x)   // contiguous rows: one linear copy runs at the full PCIe rate
-                    CUDA_TRY(cudaMemcpyAsync(sl.dx, xs, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, h->s_in));
+                    CUDA_TRY(cudaMemcpyAsync(sl.dx, xs, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, s_in));
                 else
-                    CUDA_TRY(cudaMemcpy2DAsync(sl.dx, row_x, xs, x_stride, row_x, nb, cudaMemcpyHostToDevice, h->s_in));
+                    CUDA_TRY(cudaMemcpy2DAsync(sl.dx, row_x, xs, x_stride, row_x, nb, cudaMemcpyHostToDevice, s_in));
             } else {
                 if (reused) CUDA_TRY(cudaEventSynchronize(sl.ev_in));            // px free: its DMA is done
                 parallel_copy_rows(static_cast<char *>(sl.px), row_x, xs, x_stride, row_x, nb, nthreads);
-                CUDA_TRY(cudaMemcpyAsync(sl.dx, sl.px, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, h->s_in));
+                CUDA_TRY(cudaMemcpyAsync(sl.dx, sl.px, static_cast<size_t>(nb) * row_x, cudaMemcpyHostToDevice, s_in));
             }
-            CUDA_TRY(cudaEventRecord(sl.ev_in, h->s_in));
+            CUDA_TRY(cudaEventRecord(sl.ev_in, s_in));
             CUDA_TRY(cudaStreamWaitEvent(h->s_k, sl.ev_in, 0));
             if (reused) CUDA_TRY(cudaStreamWaitEvent(h->s_k, sl.ev_out, 0));     // dy free: its copy-out is done
             if ((rc = launch(sl.dx, sl.dy, nb, h->s_k))) return rc;
@@ -771,7 +777,8 @@ int host_pipeline(smm_handle *h, const void *x, size_t row_x, size_t x_stride, v
         // nothing queued may still touch the caller's buffers (or the bounce buffers) after the
         // failure has been reported
         const std::string msg = g_err;
-        cudaStreamSynchronize(h->s_in); cudaStreamSynchronize(h->s_k); cudaStreamSynchronize(h->s_out);
+        cudaStreamSynchronize(h->s_in[0]); cudaStreamSynchronize(h->s_in[1]);
+        cudaStreamSynchronize(h->s_k); cudaStreamSynchronize(h->s_out);
         cudaGetLastError();
         g_err = msg;
         return rc;
@@ -842,7 +849,7 @@ int smm_destroy(smm_handle *h)
             for (cudaEvent_t ev : {s.ev_in, s.ev_k, s.ev_out})
                 if (ev) cudaEventDestroy(ev);
         }
-        for (cudaStream_t st : {h->s_in, h->s_k, h->s_out})
+        for (cudaStream_t st : {h->s_in[0], h->s_in[1], h->s_k, h->s_out})
             if (st) cudaStreamDestroy(st);
     }
     delete h;

@@ -25,25 +25,108 @@ def shard_sizes(B: int, world: int):
     return [batch_shard(B, world, r)[1] - batch_shard(B, world, r)[0] for r in range(world)]
 
 
-def gather_to_host(y_local, B: int, group=None, dst: Optional[int] = 0):
+class HostGather:
+    """Reusable destination of :func:`gather_to_host` with ``via="shm"``: one ``[B, ...]`` array in
+    POSIX shared memory that every rank of the box maps; each rank's slice is registered with the
+    CUDA driver once, so its block goes device -> host by DMA straight into place, all ranks in
+    parallel over their own PCIe links (no collective, no staging copy on a single rank).
+
+    Create it collectively (all ranks, same arguments); rank ``dst`` reads ``.array`` (a CPU torch
+    tensor view of the shared block).  ``close()`` collectively when done.
+    """
+
+    def __init__(self, B: int, tail, dtype, group=None, dst: int = 0, register: bool = True):
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+
+        self.B, self.tail, self.dtype, self.group, self.dst = int(B), tuple(tail), dtype, group, dst
+        dist_on = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if dist_on else 1
+        self.rank = dist.get_rank(group) if dist_on else 0
+        itemsize = torch.empty((), dtype=dtype).element_size()
+        row = int(np.prod(self.tail, dtype=np.int64)) * itemsize
+        nbytes = max(1, self.B * row)
+        name = [None]
+        if self.rank == dst:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self._shm.name
+        if dist_on:
+            dist.broadcast_object_list(name, src=dst, group=group)
+        if self.rank != dst:
+            self._shm = shared_memory.SharedMemory(name=name[0])
+            try:        # the creating rank owns the segment: keep this process's resource tracker out of it
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
+        flat = np.ndarray((nbytes,), dtype=np.uint8, buffer=self._shm.buf)
+        self.array = torch.from_numpy(flat[: self.B * row]).view(dtype).reshape((self.B,) + self.tail)
+        self.start, self.stop = batch_shard(self.B, self.world, self.rank)
+        self.mine = self.array[self.start:self.stop]
+        self._registered = None
+        if register and torch.cuda.is_available() and self.mine.numel():
+            rt = torch.cuda.cudart()
+            ptr, size = self.mine.data_ptr(), self.mine.numel() * itemsize
+            if int(rt.cudaHostRegister(ptr, size, 0)) == 0:      # else: pageable copy, still correct
+                self._registered = ptr
+        if dist_on:
+            dist.barrier(group=group)
+
+    def close(self):
+        import torch
+        import torch.distributed as dist
+        if self._registered is not None:
+            torch.cuda.cudart().cudaHostUnregister(self._registered)
+            self._registered = None
+        self.array = self.mine = None
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier(group=self.group)
+        try:
+            self._shm.close()
+            if self.rank == self.dst:
+                self._shm.unlink()
+        except Exception:
+            pass
+
+
+def gather_to_host(y_local, B: int, group=None, dst: Optional[int] = 0, via: str = "nccl", out=None):
     """Assemble the full ``[B, ...]`` result from per-rank blocks (order = rank order) -- the one
-    collective of the path, after the hot loop ("the final host gather").
+    exchange of the path, after the hot loop ("the final host gather").
 
     ``y_local``: this rank's ``[b_rank, ...]`` torch tensor (CUDA with NCCL, CPU with gloo).
-    Returns a CPU tensor on rank ``dst`` (pinned when the blocks are CUDA tensors), else ``None``;
-    ``dst=None`` returns it on every rank.  With a destination rank the blocks travel once
-    (``gather``: the device of rank ``dst`` receives the other ranks' blocks over NVLink and
-    every block is copied device->host straight into its rows of the result); ``dst=None`` uses
-    ``all_gather_into_tensor``.  Blocks shorter than ``ceil(B / world)`` rows (the last ranks)
-    are padded for the collective only.
+    Returns a CPU tensor on rank ``dst``, else ``None``; ``dst=None`` returns it on every rank.
+
+    * ``via="nccl"`` (any backend): with a destination rank the blocks travel once (``gather``: the
+      device of rank ``dst`` receives the other ranks' blocks over NVLink and every block is copied
+      device->host straight into its rows of a pinned result -- ``out`` if given); ``dst=None`` uses
+      ``all_gather_into_tensor``.  The whole result crosses ONE PCIe link.
+    * ``via="shm"`` (ranks on one box, ``out`` = a :class:`HostGather`): every rank copies its block
+      device->host into its rows of the shared array over its OWN PCIe link, then a barrier; no
+      collective moves data.
+    Blocks shorter than ``ceil(B / world)`` rows (the last ranks) are padded for the collective only.
     """
     import torch
     import torch.distributed as dist
 
-    if not (dist.is_available() and dist.is_initialized()):
+    dist_on = dist.is_available() and dist.is_initialized()
+    if via == "shm":
+        if not isinstance(out, HostGather):
+            raise ValueError('via="shm" needs out=HostGather(...) created collectively beforehand')
+        if out.mine.shape[0]:
+            out.mine.copy_(y_local[: out.mine.shape[0]], non_blocking=True)
+        if y_local.is_cuda:
+            torch.cuda.current_stream(y_local.device).synchronize()
+        if dist_on:
+            dist.barrier(group=group)
+        return out.array if (dst is None or out.rank == dst) else None
+    if via != "nccl":
+        raise ValueError('via must be "nccl" or "shm"')
+    if not dist_on:
         if not y_local.is_cuda:
             return y_local
-        host = torch.empty(tuple(y_local.shape), dtype=y_local.dtype, pin_memory=True)
+        host = out if out is not None else torch.empty(tuple(y_local.shape), dtype=y_local.dtype, pin_memory=True)
         host.copy_(y_local, non_blocking=True)
         torch.cuda.current_stream(y_local.device).synchronize()
         return host
@@ -55,15 +138,15 @@ def gather_to_host(y_local, B: int, group=None, dst: Optional[int] = 0):
         block = torch.zeros((per,) + tail, dtype=y_local.dtype, device=y_local.device)
         block[: y_local.shape[0]] = y_local
     if dst is None:
-        out = torch.empty((world * per,) + tail, dtype=y_local.dtype, device=y_local.device)
-        dist.all_gather_into_tensor(out, block, group=group)
-        return out[:B].cpu()
+        full = torch.empty((world * per,) + tail, dtype=y_local.dtype, device=y_local.device)
+        dist.all_gather_into_tensor(full, block, group=group)
+        return full[:B].cpu()
     if rank != dst:
         dist.gather(block, gather_list=None, dst=dst, group=group)
         return None
     bufs = [block if r == rank else torch.empty_like(block) for r in range(world)]
     dist.gather(block, gather_list=bufs, dst=dst, group=group)
-    host = torch.empty((B,) + tail, dtype=y_local.dtype, pin_memory=y_local.is_cuda)
+    host = out if out is not None else torch.empty((B,) + tail, dtype=y_local.dtype, pin_memory=y_local.is_cuda)
     for r in range(world):
         a, b = batch_shard(B, world, r)
         if b > a:
@@ -73,7 +156,7 @@ def gather_to_host(y_local, B: int, group=None, dst: Optional[int] = 0):
     return host
 
 
-def regrid_sharded(regridder, x, group=None, gather: bool = True, dst: Optional[int] = 0):
+def regrid_sharded(regridder, x, group=None, gather: bool = True, dst: Optional[int] = 0, via: str = "nccl", out=None):
     """Regrid this rank's block of the leading (batch) axis of ``x`` and optionally gather.
 
     ``x`` is the FULL array on every rank (or a lazily sliceable object); only
@@ -94,7 +177,7 @@ def regrid_sharded(regridder, x, group=None, gather: bool = True, dst: Optional[
     import torch
     if not isinstance(y_local, torch.Tensor):
         y_local = torch.from_numpy(y_local)
-    return gather_to_host(y_local, B, group=group, dst=dst)
+    return gather_to_host(y_local, B, group=group, dst=dst, via=via, out=out)
 
 
 def bind_to_gpu_numa(device_index: int) -> Optional[int]:

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from smmregrid_b200.shard import batch_shard, gather_to_host, shard_sizes
+from smmregrid_b200.shard import HostGather, batch_shard, gather_to_host, shard_sizes
 
 
 def test_batch_shard_partitions():
@@ -41,7 +41,14 @@ def _worker(rank, world, port, B, n_dst, q):
                    + torch.arange(n_dst, dtype=torch.float64)[None, :])
         full = gather_to_host(y_local, B, dst=0)
         everywhere = gather_to_host(y_local, B, dst=None)
-        q.put((rank, None if full is None else full.numpy(), everywhere.numpy()))
+        # shared-memory gather: every rank writes its own rows, no collective moves data
+        hg = HostGather(B, (n_dst,), torch.float64, dst=0)
+        shm = gather_to_host(y_local, B, dst=0, via="shm", out=hg)
+        shm = None if shm is None else shm.numpy().copy()
+        again = gather_to_host(y_local + 1.0, B, dst=0, via="shm", out=hg)       # the destination is reusable
+        again = None if again is None else again.numpy().copy()
+        hg.close()
+        q.put((rank, None if full is None else full.numpy(), everywhere.numpy(), shm, again))
     finally:
         dist.destroy_process_group()
 
@@ -57,8 +64,8 @@ def test_gather_world2_gloo(B):
         p.start()
     res = {}
     for _ in range(world):
-        rank, full, everywhere = q.get(timeout=120)
-        res[rank] = (full, everywhere)
+        rank, full, everywhere, shm, again = q.get(timeout=120)
+        res[rank] = (full, everywhere, shm, again)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -66,3 +73,4 @@ def test_gather_world2_gloo(B):
     assert res[1][0] is None
     assert np.array_equal(res[0][0], expect)
     assert np.array_equal(res[0][1], expect) and np.array_equal(res[1][1], expect)
+    assert res[1][2] is None and np.array_equal(res[0][2], expect) and np.array_equal(res[0][3], expect + 1.0)
