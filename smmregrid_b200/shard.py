@@ -32,7 +32,8 @@ class HostGather:
     parallel over their own PCIe links (no collective, no staging copy on a single rank).
 
     Create it collectively (all ranks, same arguments); rank ``dst`` reads ``.array`` (a CPU torch
-    tensor view of the shared block).  ``close()`` collectively when done.
+    tensor view of the shared block) and must be done with it before the ranks gather into it
+    again.  ``close()`` collectively when done.
     """
 
     def __init__(self, B: int, tail, dtype, group=None, dst: int = 0, register: bool = True):

@@ -45,6 +45,7 @@ def _worker(rank, world, port, B, n_dst, q):
         hg = HostGather(B, (n_dst,), torch.float64, dst=0)
         shm = gather_to_host(y_local, B, dst=0, via="shm", out=hg)
         shm = None if shm is None else shm.numpy().copy()
+        dist.barrier()                               # the result is consumed before the array is written again
         again = gather_to_host(y_local + 1.0, B, dst=0, via="shm", out=hg)       # the destination is reusable
         again = None if again is None else again.numpy().copy()
         hg.close()
