@@ -343,7 +343,7 @@ int64_t pick_chunks(int64_t B, int64_t blocks_total, int64_t slots, double bytes
     const double items = waves * static_cast<double>(slots);
     int64_t nchunks = static_cast<int64_t>(items / static_cast<double>(std::max<int64_t>(blocks_total, 1)) + 0.5);
     const int64_t max_chunks = std::max<int64_t>(1, B / k_min_rows);
-    nchunks = std::max<int64_t>(1, std::min(nchunks, max_chunks));
+    nchunks = std::max<int64_t>(1, std::min<int64_t>({nchunks, max_chunks, 65535}));      // (grid.y of the staged launch)
     chunk = (B + nchunks - 1) / nchunks;
     chunk = (chunk + multiple - 1) / multiple * multiple;
     return (B + chunk - 1) / chunk;
@@ -509,19 +509,21 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         a.rows_per_stage = nb_rows;
         a.stage_off = static_cast<uint32_t>(stage_off);
         const size_t smem = stage_off + S * stage_bytes;
-        int64_t item = 0;
+        // grid: x = tile, y = batch chunk, z = level of the group (blocks beyond a level's tile
+        // count exit at once).  No index arithmetic in the kernel: what steers its batch loop stays
+        // in uniform registers.
+        int64_t max_tiles = 0;
         jb.njobs = static_cast<int32_t>(g1 - g0);
         for (size_t g = g0; g < g1; ++g) {
             LevelJob &j = jb.jobs[g - g0];
             fill_job(staged[g], j);
             j.nblocks = h->levels[staged[g].level].ntiles;
-            j.item0 = static_cast<int32_t>(item);
-            item += static_cast<int64_t>(j.nblocks) * nchunks;
+            j.item0 = 0;
+            max_tiles = std::max<int64_t>(max_tiles, j.nblocks);
         }
-        if (item > INT32_MAX) return fail(SMM_ERR_INVALID, "too many work items in one launch");
         g0 = g1;
-        if (item == 0) continue;
-        const dim3 grid(static_cast<unsigned>(item));
+        if (max_tiles == 0) continue;
+        const dim3 grid(static_cast<unsigned>(max_tiles), static_cast<unsigned>(nchunks), static_cast<unsigned>(jb.njobs));
         const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, h->device, lpr, kpl, nct, packed, ord, grid, smem, st, jb, a);
         if (rc) return rc;
     }

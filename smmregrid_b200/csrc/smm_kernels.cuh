@@ -410,11 +410,14 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
     const int warp = tid >> 5;
     const int lane = tid & 31;
 
-    int jidx;
-    const LevelJob &job = find_job(jb, blockIdx.x, jidx);
-    const int local = blockIdx.x - job.item0;
-    const int tile = local % job.nblocks;
-    const int chunk = local / job.nblocks;
+    // blockIdx.y = level of the grouped launch, blockIdx.x = its work item: everything that
+    // steers the batch loop (tile, chunk, b0, b1, stage base) then derives from block indices and
+    // kernel parameters only, stays in uniform registers, and the per-link shared-memory load
+    // becomes LDS [R_off + UR_base] without a per-link address instruction
+    const LevelJob &job = jb.jobs[blockIdx.z];
+    const int tile = blockIdx.x;
+    const int chunk = blockIdx.y;
+    if (tile >= job.nblocks) return;
     const int64_t b0 = static_cast<int64_t>(chunk) * a.chunk;
     const int64_t b1 = (b0 + a.chunk < a.B) ? b0 + a.chunk : a.B;
     const TileDesc td = job.tiles[tile];
@@ -424,7 +427,7 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
     SegB *ssegs = reinterpret_cast<SegB *>(smem + kSmemHeader);
     const uint32_t smem_addr = pin_reg(smem_u32(smem));
     const uint32_t full_addr = smem_addr, empty_addr = smem_addr + 8 * kMaxStages;
-    const uint32_t stages_addr = smem_addr + a.stage_off;
+    const uint32_t stages_addr = smem_u32(smem) + a.stage_off;      // not pinned: stays uniform
     const int S = a.nstages;
 
     for (int i = tid; i < td.nseg; i += kThreads) {
@@ -491,8 +494,8 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
 #pragma unroll
             for (int k = 0; k < KPL; ++k) {
                 w[k] = __ldg(job.wplan + base + static_cast<size_t>(k) * NCT);
-                off[k] = static_cast<uint32_t>(__ldg(job.iplan + base + static_cast<size_t>(k) * NCT)) *
-                         static_cast<uint32_t>(sizeof(TX));
+                off[k] = stages_addr + static_cast<uint32_t>(__ldg(job.iplan + base + static_cast<size_t>(k) * NCT)) *
+                                           static_cast<uint32_t>(sizeof(TX));      // address of the link in stage 0, row 0
             }
         }
         if constexpr (PACKED) {
@@ -521,7 +524,7 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
             for (int64_t g = b0; g < b1; g += NB) {
                 const int nb = (g + NB <= b1) ? NB : static_cast<int>(b1 - g);
                 mbar_wait(full_addr + 8 * s, ph);
-                uint32_t sb = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
+                uint32_t sb = static_cast<uint32_t>(s) * a.stage_bytes;      // uniform: LDS [R_link + UR_sb]
 #pragma unroll 1
                 for (int n = 0; n < nb; ++n, sb += a.row_bytes, yb += a.y_bstride, xp += a.x_bstride) {
                     double s4[4] = {0.0, 0.0, 0.0, 0.0};
@@ -598,7 +601,7 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         for (int64_t g = b0; g < b1; g += NB) {          // one stage = up to NB consecutive batch rows
             const int nb = (g + NB <= b1) ? NB : static_cast<int>(b1 - g);
             mbar_wait(full_addr + 8 * s, ph);
-            uint32_t sb = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
+            uint32_t sb = static_cast<uint32_t>(s) * a.stage_bytes;          // uniform: LDS [R_link + UR_sb]
 #pragma unroll 1
             for (int n = 0; n < nb; ++n, sb += a.row_bytes, yp += a.y_bstride, xp += a.x_bstride) {
                 double acc = 0.0;
@@ -628,7 +631,7 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
                             } else {
                                 double s3[3];
                                 lane_sum_valid<TX, KPL, NCT>(job.wplan, job.iplan,
-                                                             static_cast<size_t>(tile) * KPL * NCT + tid, sb, s3);
+                                                             static_cast<size_t>(tile) * KPL * NCT + tid, stages_addr + sb, s3);
                                 acc = renormalise(group_sum<LPR>(s3[0]), group_sum<LPR>(s3[1]), group_sum<LPR>(s3[2]),
                                                   a.renorm_min_valid);
                                 renormed = true;
