@@ -473,6 +473,16 @@ def main():
             dist.barrier()
         _lib.check(lib.smm_copy_ceiling(local, yh_pin.data_ptr(), d2h_bytes, 1, 5, ctypes.byref(sec)))
         d2h_s = all_max(sec.value)
+        # the same through the C ABI alone (smm_apply_host into a preallocated pinned result):
+        # separates the pipeline inside the library from the Python layer above it
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        tc0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            _lib.check(lib.smm_apply_host(rg.weights_matrix.handle, 0, xh.data_ptr(), xcode, Be, n_src,
+                                          yh_pin.data_ptr(), ycode, n_dst, int(masked), area_min, opts, 0))
+        tc = all_max(time.perf_counter() - tc0)
         ceiling_gbs = world * h2d_bytes / h2d_s / 1e9
         e2e_h2d_gbs = world * h2d_bytes * args.e2e_steps / te / 1e9
         # second figure: PAGEABLE numpy input, what Regridder.regrid(DataArray / ndarray) is handed
@@ -489,6 +499,8 @@ def main():
                "h2d_ceiling_gbs": ceiling_gbs,
                "d2h_ceiling_gbs": world * d2h_bytes / d2h_s / 1e9,
                "frac_of_ceiling": e2e_h2d_gbs / ceiling_gbs,
+               "c_abi_only": {"h2d_gbs": world * h2d_bytes * args.e2e_steps / tc / 1e9, "ms_per_step": 1e3 * tc / args.e2e_steps,
+                              "api": "smm_apply_host(pinned x, preallocated pinned y)"},
                "ceiling": f"bare pinned cudaMemcpyAsync of the same bytes, 5 back-to-back copies, all {world} rank(s) concurrently, max over ranks",
                "pageable": {"value": world * Be * n_src * p_steps / tp, "unit": UNIT, "steps": p_steps,
                             "ms_per_step": 1e3 * tp / p_steps, "h2d_gbs": world * h2d_bytes * p_steps / tp / 1e9,

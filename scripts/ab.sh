@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B helper for the GPU box: ab.sh <label> <bench args...>  -> one line "label GB/s ms launches"
 label=$1; shift
-out=$(python bench.py --no-cpu --no-e2e "$@" 2>gpurun_out/ab_err.log | tail -1)
+out=$(python bench.py --no-cpu --no-e2e --no-others --strong-rows 0 "$@" 2>gpurun_out/ab_err.log | tail -1)
 python - "$label" "$out" <<'PY'
 import json, sys
 try:

@@ -1,11 +1,20 @@
 #!/bin/bash
-# Round evidence on the GPU box: tests, hypothesis soak, both bench arms, ncu launch list.
-# Usage: gpurun -- bash scripts/round_evidence.sh   (outputs under gpurun_out/, copied to profiles/ by hand)
+# Round evidence on the GPU box (one GPU): tests, both bench arms, the launch list of the bench
+# command and `ncu --set full` captures of the dominant kernel of C4 / C2 / C3 / C5dis.
+# Usage: gpurun -- bash scripts/round_evidence.sh <tag>     (outputs under gpurun_out/; summaries are
+# made here afterwards with scripts/ncu_summary.py and scripts/make_traffic.py and copied to profiles/)
+tag=${1:-r02}
 mkdir -p gpurun_out
-set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-SMM_HYP_EXAMPLES=150 python -m pytest tests/test_gpu_properties.py -m gpu -x -q 2>&1 | tail -3
-python bench.py --impl reference > gpurun_out/r01i_bench_reference.json 2> gpurun_out/r01i_bench_reference.err; tail -c 600 gpurun_out/r01i_bench_reference.json
-python bench.py > gpurun_out/r01i_bench_c4_n1.json 2> gpurun_out/r01i_bench_c4_n1.err; tail -c 1500 gpurun_out/r01i_bench_c4_n1.json
-python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/c4_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01i_launches_c4.csv python bench.py --steps 3 --warmup 3 --no-cpu --no-e2e > gpurun_out/c4_launches.log 2>&1
+Q="--steps 3 --warmup 3 --no-cpu --no-e2e --no-others --strong-rows 0"
+python -m pytest tests -m gpu -q --no-header > gpurun_out/${tag}_pytest.log 2>&1; tail -3 gpurun_out/${tag}_pytest.log
+python bench.py --impl reference > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err
+python bench.py > gpurun_out/${tag}_bench_c4_n1.json 2> gpurun_out/${tag}_bench_c4_n1.err; tail -c 800 gpurun_out/${tag}_bench_c4_n1.json
+python bench.py $Q > gpurun_out/${tag}_plain_c4.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_c4.csv \
+    python bench.py $Q > gpurun_out/${tag}_launches_c4.log 2>&1
+for wl in C4 C2 C3 C5dis; do
+  python bench.py --workload $wl $Q > gpurun_out/${tag}_plain_${wl}.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:'staged_kernel|compact' -s 6 -c 2 -f \
+      -o gpurun_out/${tag}_${wl} python bench.py --workload $wl $Q > gpurun_out/${tag}_ncu_${wl}.log 2>&1
+done
+ls -la gpurun_out | tail -20

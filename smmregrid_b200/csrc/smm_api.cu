@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -672,6 +673,11 @@ template <typename Launch>
 int host_pipeline(smm_handle *h, const void *x, size_t row_x, size_t x_stride, void *y, size_t row_y,
                   size_t y_stride, int64_t B, int64_t chunk_rows, Launch launch)
 {
+    static const bool k_trace = env_int("SMM_HOST_TRACE", 0) != 0;      // diagnostics: phase times on stderr
+    const auto t_enter = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
     const bool x_pinned = is_pinned(x), y_pinned = is_pinned(y);
     if (chunk_rows <= 0) {
         // ~128 MB of source per chunk for direct DMA (the fill of the pipeline -- the first chunk's
@@ -774,7 +780,12 @@ int host_pipeline(smm_handle *h, const void *x, size_t row_x, size_t x_stride, v
             if ((rc = drain(s))) return rc;
         return SMM_OK;
     };
+    const double ms_setup = ms_since(t_enter);
     const int rc = run();
+    if (k_trace)
+        std::fprintf(stderr, "[smm host pipeline] B=%lld chunk_rows=%lld slots=%d pinned x/y=%d/%d setup %.3f ms total %.3f ms (%.2f GB/s in)\n",
+                     static_cast<long long>(B), static_cast<long long>(chunk_rows), nslots, int(x_pinned), int(y_pinned), ms_setup,
+                     ms_since(t_enter), static_cast<double>(B) * row_x / (ms_since(t_enter) * 1e6));
     if (rc) {
         // nothing queued may still touch the caller's buffers (or the bounce buffers) after the
         // failure has been reported
