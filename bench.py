@@ -494,7 +494,7 @@ def main():
         e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": d2h_bytes, "batch_rows_per_step": Be, "steps": args.e2e_steps,
                "ms_per_step": 1e3 * te / args.e2e_steps,
-               "api": "Regridder.regrid(pinned host tensor) -> smm_apply_host", "numa_node": numa,
+               "api": "Regridder.regrid(pinned host tensor) -> smm_apply_host -> new host array", "numa_node": numa,
                "h2d_gbs": e2e_h2d_gbs,
                "h2d_ceiling_gbs": ceiling_gbs,
                "d2h_ceiling_gbs": world * d2h_bytes / d2h_s / 1e9,

@@ -605,7 +605,7 @@ int host_threads()
     cpu_set_t set;
     int n = 1;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
-    return std::max(1, std::min(n, env_int("SMM_HOST_COPY_THREADS", 8)));
+    return std::max(1, std::min(n, env_int("SMM_HOST_COPY_THREADS", 12)));
 }
 
 // rows x row_bytes strided copy split over a few threads (pageable <-> pinned staging)

@@ -327,7 +327,7 @@ class Regridder(object):
                 raise ValueError("out= needs transpose=True and a C-contiguous array")
             y = torch.from_numpy(out.reshape(T, Ld, self.n_dst))
         else:
-            y = torch.empty((T, Ld, self.n_dst), dtype=self._out_torch_dtype(x.dtype), pin_memory=True)
+            y = torch.from_numpy(np.empty((T, Ld, self.n_dst), dtype=self._out_np_dtype()))
         _lib.check(_lib.load().smm_apply_levels_host(
             self.weights_matrix.handle, Ld, widx.ctypes.data_as(ctypes.c_void_p),
             ctypes.c_void_p(x.data_ptr()), _np_dtype_code(_np_of(x.dtype)), T,
@@ -370,7 +370,10 @@ class Regridder(object):
                     raise ValueError("out= must be a C-contiguous array")
                 y = torch.from_numpy(out.reshape(B, self.n_dst))
             else:
-                y = torch.empty((B, self.n_dst), dtype=self._out_torch_dtype(xt.dtype), pin_memory=True)
+                # pageable, untouched memory: the library returns the (50-100x smaller) result through
+                # its own pinned bounce buffers, overlapped with the transfers still in flight -- a
+                # pinned allocation per call would cost more than that (3.6 ms for 66 MB, measured)
+                y = torch.from_numpy(np.empty((B, self.n_dst), dtype=self._out_np_dtype()))
             _lib.check(lib.smm_apply_host(
                 parent.handle, lvl, ctypes.c_void_p(xt.data_ptr()), _np_dtype_code(_np_of(xt.dtype)), B,
                 self.n_src, ctypes.c_void_p(y.data_ptr()), _np_dtype_code(_np_of(y.dtype)), self.n_dst,
