@@ -111,7 +111,8 @@ typedef struct smm_info {
     int64_t touched_src;         /* distinct source columns with >= 1 link                */
     int64_t device_bytes;        /* device memory held for this level                     */
     int32_t plan_cache_hit;      /* 1: CSR + plan came from smm_create_opts.plan_cache_dir */
-    int32_t reserved;
+    int32_t gather_rows;         /* split plan: rows longer than the packed layout's 16 links, served */
+                                 /* by the gather kernel next to the staged launch (0: none)          */
 } smm_info;
 
 /*
@@ -249,6 +250,8 @@ int smm_host_plan_copy(const smm_host_plan *p, int32_t *rowptr, int32_t *col, do
                        int32_t *tiles, uint32_t *segs, double *wplan, uint16_t *iplan);
 /* rowmap [n_dst]: destination row held by every tile slot (only when info.rows_reordered). */
 int smm_host_plan_rowmap(const smm_host_plan *p, int32_t *rowmap);
+/* rows [info.gather_rows]: the long rows of a split plan, ascending. */
+int smm_host_plan_gather_rows(const smm_host_plan *p, int32_t *rows);
 /* rowslot [n_tiles*4*consumer_threads] (only when info.packed_rows): destination row whose value
  * starts in sub-row u (link slots 4u..4u+3) of thread t at [tile][u][t]; -1 none, -2 the sub-row
  * continues the row of sub-row u-1. */

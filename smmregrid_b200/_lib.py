@@ -32,7 +32,7 @@ class SmmInfo(ctypes.Structure):
         ("rows_per_tile", i32), ("n_tiles", i32), ("max_row_nnz", i32), ("max_tile_segments", i32),
         ("consumer_threads", i32), ("rows_reordered", i32), ("packed_rows", i32), ("summation", i32),
         ("max_tile_elems", i64), ("sum_tile_elems", i64), ("touched_src", i64), ("device_bytes", i64),
-        ("plan_cache_hit", i32), ("reserved", i32),
+        ("plan_cache_hit", i32), ("gather_rows", i32),
     ]
 
     def asdict(self):
@@ -89,6 +89,7 @@ SIGNATURES = {
     "smm_host_plan_copy": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "smm_host_plan_rowmap": (ctypes.c_int, [vp, vp]),
     "smm_host_plan_rowslot": (ctypes.c_int, [vp, vp]),
+    "smm_host_plan_gather_rows": (ctypes.c_int, [vp, vp]),
     "smm_host_plan_compact": (ctypes.c_int, [vp, P(i64), P(i64), vp, vp, vp]),
     "smm_host_plan_free": (None, [vp]),
     "smm_copy_ceiling": (ctypes.c_int, [i32, vp, i64, i32, i32, P(f64)]),

@@ -96,7 +96,7 @@ void free_level(LevelDev &L)
     cudaFree(L.rowptr); cudaFree(L.col); cudaFree(L.val);
     cudaFree(L.tiles); cudaFree(L.segs); cudaFree(L.wplan); cudaFree(L.iplan); cudaFree(L.rowmap);
     cudaFree(L.imask); cudaFree(L.frac);
-    cudaFree(L.tcols); cudaFree(L.blk_ptr); cudaFree(L.rcol);
+    cudaFree(L.tcols); cudaFree(L.blk_ptr); cudaFree(L.rcol); cudaFree(L.gather_rows);
     L = LevelDev{};
 }
 
@@ -124,6 +124,11 @@ int upload_level(const HostCsr &csr, const HostPlan &plan, LevelDev &L)
         L.reordered = plan.reordered;
         if (plan.packed) { if ((rc = upload(&L.rowmap, plan.rowslot, L.device_bytes))) return rc; }
         else if (!plan.rowmap.empty() && (rc = upload(&L.rowmap, plan.rowmap, L.device_bytes))) return rc;
+        L.n_gather_rows = static_cast<int32_t>(plan.gather_rows.size());
+        if (L.n_gather_rows > 0) {
+            if ((rc = upload(&L.gather_rows, plan.gather_rows, L.device_bytes))) return rc;
+            for (int32_t r : plan.gather_rows) L.gather_nnz += csr.rowptr[r + 1] - csr.rowptr[r];
+        }
     }
     if (!plan.ok && L.nnz > 0) {
         // scattered sources: the two-pass compact path needs the touched columns and link ranks
@@ -204,26 +209,60 @@ int host_threads_all()
     return sched_getaffinity(0, sizeof(set), &set) == 0 ? std::max(1, CPU_COUNT(&set)) : 1;
 }
 
-// Tile plans of all levels.  A packed tile holds 4x the rows, so its footprint may not fit where
-// the lane-per-row tile's does: if any level's packed plan is unusable, all levels fall back to
-// the lane-per-row layout (one kernel per grouped launch).
+// Tile plans of all levels, one layout for the whole weight set so that a grouped launch runs a
+// single kernel.  Candidates, in order of preference:
+//   packed        every row has <= 16 links: a thread owns up to 4 rows;
+//   split         a few rows are longer (at most 1/8 of the rows, 40 % of the links: the fans of
+//                 cells around the grid poles of a tripolar ocean grid): the short rows are packed,
+//                 the long ones are listed for the gather kernel (HostPlan::gather_rows);
+//   lanes per row from the longest row.
+// A packed tile holds 4x the rows, so its footprint may not fit where the lane-per-row tile's
+// does: if any level's packed plan is unusable for that reason, all levels fall back to the next
+// candidate.
 void plan_levels(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, bool ref_order,
                  std::vector<HostPlan> &plans)
 {
     PlanChoice pc = choose_plan(csrs, n_dst, sm_count, ref_order);
     plans.assign(csrs.size(), HostPlan{});
+    bool split = false;
+    if (pc.cfg && !pc.packed) {
+        int64_t rows = 0, rows_long = 0, nnz = 0, nnz_long = 0;
+        for (const HostCsr &c : csrs)
+            for (int64_t r = 0; r < c.n_dst; ++r) {
+                const int32_t n = c.rowptr[r + 1] - c.rowptr[r];
+                ++rows; nnz += n;
+                if (n > 16) { ++rows_long; nnz_long += n; }
+            }
+        split = rows_long > 0 && rows_long * 8 <= rows && nnz_long * 5 <= nnz * 2;
+        if (const char *e = std::getenv("SMM_SPLIT")) split = rows_long > 0 && e[0] == '1';      // experiments: 0 | 1
+    }
     // levels are independent: a few host threads take them in turn (75 ocean levels: ~13 s -> ~1 s)
     const int nthreads = std::max(1, std::min({host_threads_all(), 16, static_cast<int>(csrs.size())}));
-    for (int pass = 0; pass < 2; ++pass) {
+    enum Mode { kSplit, kPacked, kLanes };
+    std::vector<Mode> modes;
+    if (split) modes.push_back(kSplit);
+    if (pc.packed) modes.push_back(kPacked);
+    modes.push_back(kLanes);
+    for (Mode mode : modes) {
+        const int32_t nct = mode == kLanes ? (ref_order ? 256 : default_consumer_threads(n_dst, pc.cfg ? pc.lpr : 0, sm_count))
+                                           : (ref_order ? 256 : default_consumer_threads(0, 1, sm_count));
         std::atomic<size_t> next{0};
         std::atomic<bool> retry{false};
         auto work = [&]() {
             for (size_t i = next.fetch_add(1); i < csrs.size() && !retry.load(); i = next.fetch_add(1)) {
                 plans[i] = HostPlan{};
                 if (!pc.cfg) { plans[i].why = "a destination row has more than 512 links"; continue; }
-                build_plan(csrs[i], pc.packed ? -1 : pc.lpr, pc.kpl, pc.nct, ref_order, plans[i]);
-                // only a footprint that is too large can be cured by smaller tiles
-                if (pc.packed && !plans[i].ok && plans[i].why.rfind("tile footprint", 0) == 0) retry.store(true);
+                if (mode == kSplit) {
+                    std::vector<int32_t> lrows, srows;
+                    long_rows(csrs[i], lrows, srows);
+                    build_plan(csrs[i], -1, pc.kpl, nct, ref_order, plans[i], &srows);
+                    plans[i].gather_rows = std::move(lrows);
+                    if (!plans[i].ok) retry.store(true);           // any failure: the whole set takes the next layout
+                } else {
+                    build_plan(csrs[i], mode == kPacked ? -1 : pc.lpr, pc.kpl, nct, ref_order, plans[i]);
+                    // only a footprint that is too large can be cured by smaller tiles
+                    if (mode == kPacked && !plans[i].ok && plans[i].why.rfind("tile footprint", 0) == 0) retry.store(true);
+                }
             }
         };
         if (nthreads == 1) {
@@ -234,8 +273,6 @@ void plan_levels(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, 
             for (auto &th : pool) th.join();
         }
         if (!retry.load()) return;
-        pc.packed = false;
-        pc.nct = ref_order ? 256 : default_consumer_threads(n_dst, pc.lpr, sm_count);
     }
 }
 
@@ -418,7 +455,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
     auto staged_smem = [&](size_t max_segs, size_t max_elems, size_t nstages) {
         return kSmemHeader + round_up(max_segs * sizeof(Seg), 128) + nstages * round_up(max_elems * sx, 128);
     };
-    std::vector<JobSpec> staged, gather;
+    std::vector<JobSpec> staged, gather, gather_lists;      // gather_lists: the long rows of split plans
     for (const JobSpec &s : specs) {
         const LevelDev &L = h->levels[s.level];
         if (s.masked && !L.has_imask)
@@ -441,6 +478,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
                                              (L.staged ? std::string("slab alignment / footprint size")
                                                        : L.why_not_staged));
         (ok ? staged : gather).push_back(s);
+        if (ok && L.n_gather_rows > 0) gather_lists.push_back(s);
     }
 
     ApplyArgs a{};
@@ -456,7 +494,7 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         j.tiles = L.tiles; j.segs = L.segs; j.wplan = L.wplan; j.iplan = L.iplan; j.rowmap = L.rowmap;
         j.rowptr = L.rowptr; j.col = L.col; j.val = L.val;
         j.imask = L.imask; j.frac = L.frac;
-        j.x = s.x; j.y = s.y; j.masked = s.masked; j.pad = 0;
+        j.x = s.x; j.y = s.y; j.masked = s.masked; j.nrows = 0;
     };
 
     // ---- staged launches: up to kMaxJobs levels at a time (balanced when there are more), and a
@@ -551,23 +589,28 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         gather.swap(plain);
     }
 
-    // ---- gather launches
-    for (size_t g0 = 0; g0 < gather.size(); g0 += kMaxJobs) {
-        const size_t g1 = std::min(gather.size(), g0 + kMaxJobs);
+    // ---- gather launches: whole levels, then the row lists of split plans
+    for (int pass = 0; pass < 2; ++pass) {
+    const std::vector<JobSpec> &list = pass == 0 ? gather : gather_lists;
+    const bool lists = pass == 1;
+    for (size_t g0 = 0; g0 < list.size(); g0 += kMaxJobs) {
+        const size_t g1 = std::min(list.size(), g0 + kMaxJobs);
         JobBatch jb{};
         int64_t nnz = 0, rows = 0;
         for (size_t g = g0; g < g1; ++g) {
-            const LevelDev &L = h->levels[gather[g].level];
-            nnz += L.nnz; rows += L.n_dst;
+            const LevelDev &L = h->levels[list[g].level];
+            nnz += lists ? L.gather_nnz : L.nnz;
+            rows += lists ? L.n_gather_rows : L.n_dst;
             a.n_src = L.n_src; a.n_dst = L.n_dst;
         }
         const double avg = rows ? static_cast<double>(nnz) / rows : 0.0;
         // reference order: one thread walks a row's links in sequence
         const int lpr = ord ? 1 : (avg <= 2.0 ? 1 : (avg <= 24.0 ? 4 : 32));
         const int rpb = kGatherThreads / lpr;
+        auto rows_of = [&](const LevelDev &L) -> int64_t { return lists ? L.n_gather_rows : L.n_dst; };
         int64_t blocks_total = 0;
         for (size_t g = g0; g < g1; ++g)
-            blocks_total += (h->levels[gather[g].level].n_dst + rpb - 1) / rpb;
+            blocks_total += (rows_of(h->levels[list[g].level]) + rpb - 1) / rpb;
         int64_t chunk = 0;
         // gather kernel: up to 8 CTAs of 256 threads per SM, a light prologue, traffic dominated by the gathers
         const double row_bytes_hbm = static_cast<double>(nnz) * 64.0 + static_cast<double>(rows) * (y_dtype == SMM_F32 ? 4 : 8);
@@ -578,16 +621,20 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         int64_t item = 0;
         jb.njobs = static_cast<int32_t>(g1 - g0);
         for (size_t g = g0; g < g1; ++g) {
+            const LevelDev &L = h->levels[list[g].level];
             LevelJob &j = jb.jobs[g - g0];
-            fill_job(gather[g], j);
-            j.nblocks = static_cast<int32_t>((h->levels[gather[g].level].n_dst + rpb - 1) / rpb);
+            fill_job(list[g], j);
+            if (lists) { j.rowmap = L.gather_rows; j.nrows = L.n_gather_rows; }
+            j.nblocks = static_cast<int32_t>((rows_of(L) + rpb - 1) / rpb);
             j.item0 = static_cast<int32_t>(item);
             item += static_cast<int64_t>(j.nblocks) * nchunks;
         }
         if (item > INT32_MAX) return fail(SMM_ERR_INVALID, "too many work items in one launch");
+        if (item == 0) continue;
         const dim3 grid(static_cast<unsigned>(item));
         const int rc = SMM_DTYPE_DISPATCH(launch_gather_t, lpr, ord, grid, st, jb, a);
         if (rc) return rc;
+    }
     }
     return SMM_OK;
 }
@@ -881,6 +928,7 @@ int smm_get_info(const smm_handle *h, int32_t level, smm_info *out)
     out->kernel = L.staged ? SMM_KERNEL_STAGED : SMM_KERNEL_GATHER;
     out->summation = h->ref_order ? SMM_SUM_REFERENCE : SMM_SUM_FAST;
     out->plan_cache_hit = h->cache_hit ? 1 : 0;
+    out->gather_rows = L.staged ? L.n_gather_rows : 0;
     out->lanes_per_row = L.lpr; out->links_per_lane = L.kpl; out->rows_per_tile = L.rpt;
     out->n_tiles = L.ntiles; out->max_row_nnz = L.max_row_nnz;
     out->max_tile_segments = L.max_segs; out->max_tile_elems = L.max_elems;
@@ -1142,6 +1190,7 @@ int smm_host_plan_info(const smm_host_plan *p, smm_info *out, int64_t *n_segs_ou
     out->packed_rows = (p->plan.ok && p->plan.packed) ? 1 : 0;
     out->summation = p->plan.ref_order ? SMM_SUM_REFERENCE : SMM_SUM_FAST;
     out->plan_cache_hit = p->cache_hit ? 1 : 0;
+    out->gather_rows = p->plan.ok ? static_cast<int32_t>(p->plan.gather_rows.size()) : 0;
     out->max_tile_elems = p->plan.max_tile_elems;
     out->sum_tile_elems = p->plan.sum_tile_elems;
     out->touched_src = p->csr.touched_src;
@@ -1171,6 +1220,14 @@ int smm_host_plan_rowmap(const smm_host_plan *p, int32_t *rowmap)
 {
     if (!p || !rowmap) return fail(SMM_ERR_INVALID, "null argument");
     if (p->plan.ok && !p->plan.rowmap.empty()) std::memcpy(rowmap, p->plan.rowmap.data(), p->plan.rowmap.size() * sizeof(int32_t));
+    return SMM_OK;
+}
+
+int smm_host_plan_gather_rows(const smm_host_plan *p, int32_t *rows)
+{
+    if (!p || !rows) return fail(SMM_ERR_INVALID, "null argument");
+    if (p->plan.ok && !p->plan.gather_rows.empty())
+        std::memcpy(rows, p->plan.gather_rows.data(), p->plan.gather_rows.size() * sizeof(int32_t));
     return SMM_OK;
 }
 

@@ -54,7 +54,8 @@ struct LevelJob {
     const Seg *segs;
     const double *wplan;      // [ntiles][KPL][NCT] register image of the link weights
     const uint16_t *iplan;    // [ntiles][KPL][NCT] footprint-local element index per link
-    const int32_t *rowmap;    // destination row of every tile slot, or null: slot i of tile t is row t*R + i
+    const int32_t *rowmap;    // staged: destination row of every tile slot, or null: slot i of tile t is row t*R + i
+                              // gather: the rows this job serves (nrows of them), or null: all n_dst rows
     const int32_t *rowptr;    // CSR by destination row, columns ascending (reference order)
     const int32_t *col;
     const double *val;
@@ -65,7 +66,7 @@ struct LevelJob {
     int32_t nblocks;          // tiles (staged) or row blocks (gather) of this level
     int32_t item0;            // first work item of this level in the launch
     int32_t masked;
-    int32_t pad;
+    int32_t nrows;            // gather: length of the row list (0: every row of the level)
 };
 
 struct JobBatch {

@@ -44,6 +44,9 @@ struct LevelDev {
     bool packed = false, reordered = false;
     int32_t *tcols = nullptr, *blk_ptr = nullptr, *rcol = nullptr;   // compact (two-pass) plan of gather levels
     int32_t compact_blocks = 0;
+    int32_t *gather_rows = nullptr;     // split plans: the long rows the gather kernel serves next to the staged launch
+    int32_t n_gather_rows = 0;
+    int64_t gather_nnz = 0;
     int32_t *imask = nullptr;
     double *frac = nullptr;
     bool has_imask = false, has_frac = false;

@@ -680,9 +680,10 @@ gather_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
 
     const int tid = threadIdx.x;
     const int l_in = tid % LPR;
-    const int64_t row64 = static_cast<int64_t>(rblock) * RPB + tid / LPR;
-    const bool valid = row64 < a.n_dst;
-    const int row = valid ? static_cast<int>(row64) : 0;
+    // the job serves every row of the level, or the rows of a list (the long rows of a split plan)
+    const int64_t slot = static_cast<int64_t>(rblock) * RPB + tid / LPR;
+    const bool valid = slot < (job.nrows > 0 ? static_cast<int64_t>(job.nrows) : a.n_dst);
+    const int row = valid ? (job.nrows > 0 ? job.rowmap[slot] : static_cast<int>(slot)) : 0;
 
     int j0 = 0, j1 = 0;
     bool dead = false;

@@ -145,19 +145,26 @@ static void build_plan_rows(const HostCsr &csr, int32_t force_lpr, int32_t force
     plan.ref_order = ref_order;
     if (nct != 256 && nct != 512) nct = 256;
     int32_t lpr = force_lpr, kpl = force_kpl;
+    int32_t max_row = csr.max_row_nnz;
+    if (order) {
+        max_row = 0;
+        for (int32_t r : *order) max_row = std::max(max_row, csr.rowptr[r + 1] - csr.rowptr[r]);
+    }
     if (packed) {
-        if (csr.max_row_nnz > kSubRows * kSubLinks) { plan.why = "row too long for the packed layout"; return; }
+        if (max_row > kSubRows * kSubLinks) { plan.why = "row too long for the packed layout"; return; }
         lpr = 1; kpl = kSubRows * kSubLinks;
     } else if (lpr <= 0 || kpl <= 0) {
-        if (!choose_lanes(csr.max_row_nnz, lpr, kpl)) {
+        if (!choose_lanes(max_row, lpr, kpl)) {
             plan.why = "a destination row has more than 512 links";
             return;
         }
-    } else if (csr.max_row_nnz > lpr * kpl) {
+    } else if (max_row > lpr * kpl) {
         plan.why = "row longer than the forced lane configuration";
         return;
     }
-    const int64_t n_dst = csr.n_dst, n_src = csr.n_src;
+    // rows this plan tiles: all of them in natural order, or the given sequence (a re-ordering of
+    // all rows, or the subset one part of a split plan covers)
+    const int64_t n_dst = order ? static_cast<int64_t>(order->size()) : csr.n_dst, n_src = csr.n_src;
     const int32_t R = packed ? nct * kSubRows : nct / lpr;          // most rows a tile can hold
     auto row_at = [&](int64_t pos) -> int64_t { return order ? (*order)[pos] : pos; };
     // tile boundaries (positions in the row order); packed: also every row's (thread, sub-row)
@@ -630,6 +637,7 @@ static void build_plan_rows(const HostCsr &csr, int32_t force_lpr, int32_t force
     }
     if (order && !packed) plan.rowmap = *order;      // packed plans carry row ids in rowslot
     plan.reordered = order != nullptr;
+    plan.nrows = n_dst;
     plan.ok = true;
 }
 
@@ -664,29 +672,39 @@ bool prefer_packed(int64_t slots_packed)
     return true;
 }
 
-void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, bool ref_order, HostPlan &plan)
+void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, bool ref_order, HostPlan &plan,
+                const std::vector<int32_t> *subset)
 {
     const bool packed = force_lpr == -1;       // -1: packed layout requested (see smm_create_levels)
     if (packed) { force_lpr = 0; force_kpl = 0; }
-    build_plan_rows(csr, force_lpr, force_kpl, nct, nullptr, packed, ref_order, plan);
-    if (plan.lpr == 0 || csr.col.empty()) return;
+    build_plan_rows(csr, force_lpr, force_kpl, nct, subset, packed, ref_order, plan);
+    if (plan.lpr == 0 || csr.col.empty() || (subset && subset->empty())) return;
     // natural order good enough: footprints within 30 % of the columns actually touched
     if (plan.ok && plan_cost(plan) <= 1.3 * static_cast<double>(plan.sum_tile_cols)) return;
     // otherwise try rows sorted by the mean source address of their links
-    const int64_t n_dst = csr.n_dst;
-    std::vector<double> key(static_cast<size_t>(n_dst));
-    for (int64_t r = 0; r < n_dst; ++r) {
+    const int64_t n_rows = subset ? static_cast<int64_t>(subset->size()) : csr.n_dst;
+    std::vector<int32_t> order(static_cast<size_t>(n_rows));
+    if (subset) order = *subset; else std::iota(order.begin(), order.end(), 0);
+    std::vector<double> key(static_cast<size_t>(csr.n_dst), 1e300);
+    for (int32_t r : order) {
         const int32_t a = csr.rowptr[r], b = csr.rowptr[r + 1];
         double sum = 0.0;
         for (int32_t j = a; j < b; ++j) sum += csr.col[j];
         key[r] = b > a ? sum / (b - a) : 1e300;          // empty rows last
     }
-    std::vector<int32_t> order(static_cast<size_t>(n_dst));
-    std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return key[x] < key[y]; });
     HostPlan alt;
     build_plan_rows(csr, force_lpr, force_kpl, nct, &order, packed, ref_order, alt);
     if (alt.ok && (!plan.ok || plan_cost(alt) < 0.8 * plan_cost(plan))) plan = std::move(alt);
+}
+
+// Rows above the packed layout's 16 links, in ascending order.
+void long_rows(const HostCsr &csr, std::vector<int32_t> &long_rows_out, std::vector<int32_t> &short_rows_out)
+{
+    long_rows_out.clear();
+    short_rows_out.clear();
+    for (int64_t r = 0; r < csr.n_dst; ++r)
+        (csr.rowptr[r + 1] - csr.rowptr[r] > kSubRows * kSubLinks ? long_rows_out : short_rows_out).push_back(static_cast<int32_t>(r));
 }
 
 void build_compact(const HostCsr &csr, int32_t block_cols, CompactPlan &out)

@@ -47,6 +47,12 @@ struct HostPlan {
     bool reordered = false;        // rows were tiled in mean-source-address order
     bool packed = false;           // packed-rows plan: one thread owns up to 4 short rows (4 link slots each)
     bool ref_order = false;        // links placed for reference-order summation (lane l, slot k = link l*kpl + k)
+    int64_t nrows = 0;             // destination rows this plan covers (n_dst unless it is one part of a split plan)
+    // Split plans: operators whose rows are mostly short (<= 16 links) with a few long ones (the
+    // fan of cells around a grid pole of a tripolar ocean grid) tile the short rows with the
+    // packed layout (this plan) and leave the long rows, listed here in ascending order, to the
+    // gather kernel (a second, small launch).  Empty for ordinary plans.
+    std::vector<int32_t> gather_rows;
     std::vector<int32_t> rowslot;  // packed: [ntiles][4][nct] destination row of a sub-row, -1 empty, -2 continuation
     std::vector<double> wplan;     // [ntiles][kpl][nct]
     std::vector<uint16_t> iplan;   // [ntiles][kpl][nct]
@@ -69,7 +75,10 @@ bool choose_lanes(int32_t max_row_nnz, int32_t &lpr, int32_t &kpl);
 // force_lpr == -1 requests the packed-rows layout (see prefer_packed).
 // ref_order: place the links for the reference's summation order (see staged_kernel ORD) instead of
 // the bank-conflict-minimising free placement of the fast sums.
-void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, bool ref_order, HostPlan &plan);
+// subset (ascending row ids): tile only these rows (one part of a split plan).
+void build_plan(const HostCsr &csr, int32_t force_lpr, int32_t force_kpl, int32_t nct, bool ref_order, HostPlan &plan,
+                const std::vector<int32_t> *subset = nullptr);
+void long_rows(const HostCsr &csr, std::vector<int32_t> &long_rows_out, std::vector<int32_t> &short_rows_out);
 
 // Packed-rows layout (one thread owns up to 4 short rows): link slots it would spend on `csr`
 // (-1: a row does not fit), and whether to use it.

@@ -322,11 +322,16 @@ def test_tripolar_ocean_levels(smm_lib, oracle, cuda):
     y_ref = oracle.regrid3d_np(x, 1, w.levels, w.levels, mats, imask, w["dst_grid_frac"], masked, 0.5)
     rg = Regridder(weights=w, remap_area_min=0.5)
     info = rg.weights_matrix.info(0)
-    # the fold makes rows long (a destination cell next to a grid pole sees a whole fan of cells) ...
-    assert info["max_row_nnz"] > 30
-    # ... and the staged footprints over-read the touched columns, but by less than the 2x at
-    # which the plan builder gives a level to the gather family
-    assert info["kernel_name"] == "staged" and info["touched_src"] < info["sum_tile_elems"] < 2 * info["touched_src"]
+    # the fold makes a few rows long (a destination cell next to a grid pole sees a whole fan of
+    # cells): the plan packs the short rows and leaves the long ones to the gather kernel instead of
+    # laying every row out for the longest one
+    cnt0 = np.bincount(w["dst_address"][0, :int(w["link_length"][0])] - 1, minlength=n_dst)
+    assert info["max_row_nnz"] > 30 and info["kernel_name"] == "staged" and info["packed_rows"] == 1
+    assert info["gather_rows"] == int((cnt0 > 16).sum()) > 0
+    assert rg.weights_matrix.info(L - 1)["gather_rows"] == 0          # the deepest level has no long row left
+    n0 = smm_lib.smm_launch_count()
+    rg.regrid(torch.from_numpy(x).cuda())
+    assert smm_lib.smm_launch_count() - n0 == 2                        # packed staged launch + the row lists
     assert np.array_equal(np.asarray(rg.masked), masked)
     for kernel in (None, "gather"):
         rg.kernel = kernel
@@ -755,3 +760,41 @@ def test_group_that_does_not_fit_together_is_split(smm_lib, oracle, cuda):
     y_ref32 = oracle.regrid3d_np(x.astype(np.float32), 1, w.levels, w.levels, mats, np.ones((2, n_dst), np.int32),
                                  np.ones((2, n_dst)), np.zeros(2, bool), 0.0)
     assert_parity(y32, y_ref32, RTOL_F64, "one group")
+
+
+def test_batch_offsets_beyond_2_31_elements(smm_lib, oracle, cuda):
+    """C4 at full size with 340 batch rows and a padded row stride: element offsets into x pass
+    2**31 (and byte offsets 2**33), in the staged kernel's TMA addresses, the gather kernel's
+    pointers and the threshold replay alike.  The rows on both sides of the 2**31 boundary and the
+    last one are checked against the oracle."""
+    import torch
+    from smmregrid_b200 import _lib, synth
+    w = synth.config_weights("C4")
+    n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+    B, ldx, ldy = 340, n_src + 64, n_dst + 8
+    assert (B - 1) * ldx > 2**31 + n_src
+    first_over = -(-2**31 // ldx)                                   # first row that starts beyond 2**31 elements
+    rows = [0, first_over - 1, first_over, B - 1]
+    x = torch.empty((B, ldx), dtype=torch.float32, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for b0 in range(0, B, 20):
+        x[b0:b0 + 20].normal_(280.0, 20.0, generator=g)
+    x[first_over, 12345] = float("nan")
+    x[B - 1, 6000000:6000100] = float("inf")
+    y = torch.full((B, ldy), -5.0, dtype=torch.float64, device="cuda")
+    xh = x[rows][:, :n_src].cpu().numpy()
+    mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    y_ref = oracle.apply_weights_c(xh, mat, None, w["dst_grid_frac"], 0.5, False, nthreads=4)
+    assert np.isnan(y_ref[2]).sum() >= 1 and np.isnan(y_ref[3]).sum() >= 1
+    h = _create(smm_lib, w)
+    try:
+        for kernel in (0, 2):
+            y.fill_(-5.0)
+            _lib.check(smm_lib.smm_apply(h, 0, x.data_ptr(), 0, B, ldx, y.data_ptr(), 1, ldy, 0, 0.5,
+                                         _lib.apply_opts(kernel), None))
+            torch.cuda.synchronize()
+            got = y[rows][:, :n_dst].cpu().numpy()
+            assert_parity(got, y_ref, RTOL_F64, f"rows {rows} kernel {kernel}")
+            assert bool((y[:, n_dst:] == -5.0).all())                # padding of y untouched
+    finally:
+        smm_lib.smm_destroy(h)

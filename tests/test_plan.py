@@ -43,6 +43,9 @@ class HostPlan:
         if inf.rows_reordered and not inf.packed_rows:      # packed plans carry the rows in rowslot
             self.rowmap = np.empty(n_dst, np.int32)
             _lib.check(lib.smm_host_plan_rowmap(h, self.rowmap.ctypes.data))
+        self.gather_rows = np.empty(inf.gather_rows, np.int32)
+        if inf.gather_rows:
+            _lib.check(lib.smm_host_plan_gather_rows(h, self.gather_rows.ctypes.data))
         self.rowslot = None
         if inf.packed_rows:
             self.rowslot = np.empty((nt, 4, nct), np.int32)
@@ -87,7 +90,17 @@ class HostPlan:
                 y[:, row0:row0 + nrows] = rows[:, :nrows]
             else:
                 y[:, self.rowmap[row0:row0 + nrows]] = rows[:, :nrows]
+        self._gather_rows_into(y, x)                   # (ascending source, separate multiply and add: reference order)
         return y
+
+    def _gather_rows_into(self, y, x):
+        """split plans: the long rows are served by the gather kernel straight from the CSR"""
+        for r in self.gather_rows:
+            a, b = self.rowptr[r], self.rowptr[r + 1]
+            acc = np.zeros(x.shape[0])
+            for j in range(a, b):
+                acc = acc + x[:, self.col[j]] * self.val[j]
+            y[:, r] = acc
 
     def emulate(self, x):
         """What staged_kernel computes for filled input x [B, n_src] (float64 math)."""
@@ -114,6 +127,7 @@ class HostPlan:
                 y[:, row0:row0 + nrows] = rows[:, :nrows]
             else:                                      # row0 = first tile slot in the re-ordered sequence
                 y[:, self.rowmap[row0:row0 + nrows]] = rows[:, :nrows]
+        self._gather_rows_into(y, x)
         return y
 
 
@@ -445,3 +459,32 @@ def test_plan_cache_round_trip(smm_lib, tmp_path):
     assert HostPlan(*args, cache_dir=d).info["plan_cache_hit"] == 1
     # an unwritable directory only disables the cache
     assert HostPlan(*args, cache_dir="/proc/definitely/not/writable").info["plan_cache_hit"] == 0
+
+
+def test_split_plan_for_mostly_short_rows(smm_lib, oracle):
+    """A tripolar (north-fold) ocean grid: nearly all destination rows have a handful of links, the
+    cells next to the grid poles collect dozens.  The plan packs the short rows (a thread owns up
+    to four of them) and lists the long ones for the gather kernel instead of laying EVERY row out
+    for the longest one; emulating both parts reproduces the oracle.  Operators whose rows are all
+    long (remapcon 0.1 -> 1 deg) or all short are planned as before."""
+    from smmregrid_b200 import synth
+    w = synth.tripolar_weights(181, 146, 180, 90)
+    n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
+    plan = HostPlan(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    info = plan.info
+    counts = np.bincount(w["dst_address"] - 1, minlength=n_dst)
+    assert info["max_row_nnz"] > 16 and info["kernel_name"] == "staged" and info["packed_rows"] == 1
+    assert info["gather_rows"] == int((counts > 16).sum()) > 0
+    assert np.array_equal(plan.gather_rows, np.flatnonzero(counts > 16))
+    listed = plan.rowslot[plan.rowslot >= 0]
+    assert np.array_equal(np.sort(listed), np.flatnonzero(counts <= 16))        # every short row exactly once
+    x = np.random.default_rng(0).standard_normal((3, n_src))
+    mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False)
+    assert_parity(plan.emulate(x), y_ref, 1e-12, "split plan")
+    # unchanged decisions elsewhere
+    for cfg, scale, packed in (("C4", 10, 0), ("C2", 8, 0), ("C1", 1, 1)):
+        wc = synth.config_weights(cfg, scale)
+        pc = HostPlan(smm_lib, wc["src_address"], wc["dst_address"], wc["remap_matrix"],
+                      wc.sizes["src_grid_size"], wc.sizes["dst_grid_size"])
+        assert pc.info["gather_rows"] == 0 and pc.info["packed_rows"] == packed, cfg
