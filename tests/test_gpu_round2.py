@@ -310,8 +310,8 @@ def test_tripolar_ocean_levels(smm_lib, oracle, cuda):
     the grid poles collect dozens of links.  Per-level oracle parity, device and host paths."""
     import torch
     from smmregrid_b200 import Regridder, synth
-    w = synth.config_weights("C3tri", 2)                     # 181 x 146 source, 37 levels -> r180x90
-    L, n_src, n_dst, T = 37, 181 * 146, 180 * 90, 5
+    w = synth.config_weights("C3tri")                        # 362 x 292 source, 75 levels -> r360x180
+    L, n_src, n_dst, T = 75, 362 * 292, 360 * 180, 3
     assert w["link_length"].size == L
     x = synth.synthetic_field((T, L, n_src), np.float32, seed=4)
     x[:, w["src_grid_imask"] == 0] = np.nan
@@ -340,9 +340,25 @@ def test_tripolar_ocean_levels(smm_lib, oracle, cuda):
     rg.kernel = None
     assert_parity(rg.regrid(x).reshape(T, L, n_dst), y_ref, RTOL_F64, "tripolar host")
     # 2-D weights of the same grid: rows of the fold region against rows of the regular region
-    w2 = synth.tripolar_weights(181, 146, 180, 90)
-    cnt = np.bincount(w2["dst_address"] - 1, minlength=n_dst).reshape(90, 180)
-    assert cnt[80:].max() > 4 * cnt[20:60].max()
+    w2 = synth.tripolar_weights(362, 292, 360, 180)
+    cnt = np.bincount(w2["dst_address"] - 1, minlength=n_dst).reshape(180, 360)
+    assert cnt[160:].max() > 4 * cnt[40:120].max()
+    # a source whose rows are not 16-byte multiples (181 x 146 cells) cannot be staged by TMA: the
+    # whole operator takes the gather kernel, long rows included -- same results
+    ws = synth.config_weights("C3tri", 2)
+    ns, nd, Ls = 181 * 146, 180 * 90, 37
+    xs = synth.synthetic_field((2, Ls, ns), np.float32, seed=5)
+    xs[:, ws["src_grid_imask"] == 0] = np.nan
+    ms = oracle.compute_weights_matrix3d_np(ws["src_address"], ws["dst_address"], ws["remap_matrix"],
+                                            ws["link_length"], ns, nd, builder=oracle.compute_weights_matrix_c)
+    ims = np.stack([oracle.mask_tensordot_c(ws["src_grid_imask"][l], ms[l])[0] for l in range(Ls)])
+    ys_ref = oracle.regrid3d_np(xs, 1, ws.levels, ws.levels, ms, ims, ws["dst_grid_frac"], oracle.check_mask_np(ims), 0.5)
+    rgs = Regridder(weights=ws, remap_area_min=0.5)
+    assert rgs.weights_matrix.info(0)["gather_rows"] > 0
+    n0 = smm_lib.smm_launch_count()
+    ys = rgs.regrid(torch.from_numpy(xs).cuda()).cpu().numpy().reshape(2, Ls, nd)
+    assert smm_lib.smm_launch_count() - n0 == 1
+    assert_parity(ys, ys_ref, RTOL_F64, "unaligned tripolar")
 
 
 # ------------------------------------------------------------------ API behaviour
@@ -779,8 +795,8 @@ def test_batch_offsets_beyond_2_31_elements(smm_lib, oracle, cuda):
     g = torch.Generator(device="cuda").manual_seed(5)
     for b0 in range(0, B, 20):
         x[b0:b0 + 20].normal_(280.0, 20.0, generator=g)
-    x[first_over, 12345] = float("nan")
-    x[B - 1, 6000000:6000100] = float("inf")
+    x[first_over, :36000] = float("nan")          # the ten source rows under the first destination row
+    x[B - 1, -36000:] = float("inf")              # ... and under the last one
     y = torch.full((B, ldy), -5.0, dtype=torch.float64, device="cuda")
     xh = x[rows][:, :n_src].cpu().numpy()
     mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
