@@ -281,11 +281,12 @@ def other_configs(dev, peak):
     specs = [("C2", "C2", 3441, "none"), ("C2 + static land mask (35 % of sources NaN)", "C2", 3441, "land"),
              ("C3", "C3", 96, "levels"), ("C3 on a tripolar (north-fold) index space", "C3tri", 96, "levels"),
              ("C2 bicubic-like (16 links/row, both signs: reference-order sums)", "C2bic", 3441, "none"),
-             ("C5nn", "C5nn", 64, "none"), ("C5dis", "C5dis", 64, "none")]
-    for label, name, B, nan in specs:
+             ("C5nn", "C5nn", 64, "none"), ("C5dis", "C5dis", 64, "none"),
+             ("C4 with reference-order sums forced (bit-identical values; SMM_SUM_REFERENCE)", "C4", 256, "none", "reference")]
+    for label, name, B, nan, *rest in specs:
         t_build = time.perf_counter()
         w, _, desc = workload(name)
-        rg = Regridder(weights=w, remap_area_min=0.5, device=dev.index)
+        rg = Regridder(weights=w, remap_area_min=0.5, device=dev.index, summation=rest[0] if rest else None)
         t_build = time.perf_counter() - t_build
         L = rg.weights_matrix.n_levels
         infos = [rg.weights_matrix.info(l) for l in range(L)]
