@@ -12,9 +12,11 @@ python bench.py > gpurun_out/${tag}_bench_c4_n1.json 2> gpurun_out/${tag}_bench_
 python bench.py $Q > gpurun_out/${tag}_plain_c4.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches_c4.csv \
     python bench.py $Q > gpurun_out/${tag}_launches_c4.log 2>&1
-for wl in C4 C2 C3 C5dis; do
+# (3 warm-up + 3 timed applies per run: skip the first 3 matching launches, keep the next two --
+# for the two-pass compact path that is one launch of each of its kernels)
+for wl in C4 C2 C3 C3tri C5dis C5nn; do
   python bench.py --workload $wl $Q > gpurun_out/${tag}_plain_${wl}.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:'staged_kernel|compact' -s 6 -c 2 -f \
+  ncu --set full --clock-control none --import-source on -k regex:'staged_kernel|compact|gather_kernel' -s 3 -c 2 -f \
       -o gpurun_out/${tag}_${wl} python bench.py --workload $wl $Q > gpurun_out/${tag}_ncu_${wl}.log 2>&1
 done
 ls -la gpurun_out | tail -20

@@ -804,6 +804,8 @@ def test_batch_offsets_beyond_2_31_elements(smm_lib, oracle, cuda):
     assert np.isnan(y_ref[2]).sum() >= 1 and np.isnan(y_ref[3]).sum() >= 1
     h = _create(smm_lib, w)
     try:
+        fr = np.ascontiguousarray(w["dst_grid_frac"], np.float64)
+        _lib.check(smm_lib.smm_set_dst_mask(h, 0, None, fr.ctypes.data))
         for kernel in (0, 2):
             y.fill_(-5.0)
             _lib.check(smm_lib.smm_apply(h, 0, x.data_ptr(), 0, B, ldx, y.data_ptr(), 1, ldy, 0, 0.5,
