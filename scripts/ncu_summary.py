@@ -12,6 +12,8 @@ METRICS = [
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum", "lts__t_sectors_srcunit_tex_op_read.sum",
+    "lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum",
     "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__block_size",
     "launch__grid_size", "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers",
     "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -35,14 +37,18 @@ def main():
     rep = sys.argv[1]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
     for line in sys.argv[2:]:
         print("# " + line)
-    print("# kernel: " + vals[col["Kernel Name"]])
-    for m in METRICS:
-        if m in col:
-            print(f"{m:<75} {units[col[m]]:<12} {vals[col[m]]}")
+    for vals in rows[2:]:                      # one block per captured launch
+        if len(vals) < len(hdr):
+            continue
+        print("# kernel: " + vals[col["Kernel Name"]])
+        for m in METRICS:
+            if m in col:
+                print(f"{m:<75} {units[col[m]]:<12} {vals[col[m]]}")
+        print()
 
 
 if __name__ == "__main__":

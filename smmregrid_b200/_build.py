@@ -44,19 +44,23 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the library if sources are newer than the binary.  Returns its path."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, variant: str = "", flags=()) -> str:
+    """Compile the library if sources are newer than the binary.  Returns its path.
+    ``variant`` / ``flags``: an experimental build with extra nvcc flags (``-DSMM_...``) next to
+    the default one, as ``lib/libsmmregrid_b200_<variant>.so`` (select it with ``SMM_LIB_PATH``)."""
+    lib_path = LIB_PATH if not variant else os.path.join(LIB_DIR, f"libsmmregrid_b200_{variant}.so")
+    obj_dir = OBJ_DIR if not variant else OBJ_DIR + "_" + variant
+    if not variant and not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + list(flags)
     if os.environ.get("SMM_NVCC_FLAGS"):
         extra += os.environ["SMM_NVCC_FLAGS"].split()
 
     def compile_one(src):
-        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", "-o", obj, os.path.join(CSRC, src)]
         proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         return src, obj, proc.returncode, proc.stdout
@@ -67,16 +71,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     bad = [src for src, _, rc, _ in results if rc != 0]
     if bad:
         raise RuntimeError(f"nvcc failed on {bad}:\n" + log)
-    tmp = LIB_PATH + ".tmp"
+    tmp = lib_path + ".tmp"
     proc = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] +
                           [obj for _, obj, _, _ in results],
                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n" + proc.stdout)
-    os.replace(tmp, LIB_PATH)
+    os.replace(tmp, lib_path)
     if verbose:
         print(log)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

@@ -788,13 +788,17 @@ compact_kernel(const TX *__restrict__ x, int64_t x_bstride, int64_t n_src, int b
     const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kCompactW;
     const int w = static_cast<int>((n_src - c0 < kCompactW) ? n_src - c0 : kCompactW);
     const int tid = threadIdx.x;
-    for (int col = tid; col < w; col += kCompactThreads) {
-        // asynchronous element copies straight into shared memory (LDGSTS): all bc rows of this
+    // thread (col, row group): the threads of a warp copy 32 consecutive columns of one batch row
+    // (one 128-byte line per LDGSTS instruction); with fewer than 256 columns per block the
+    // remaining threads take every (256 / W)-th batch row
+    constexpr int kRowGroups = kCompactThreads / kCompactW > 0 ? kCompactThreads / kCompactW : 1;
+    for (int col = tid % kCompactW; col < w; col += kCompactThreads) {
+        // asynchronous element copies straight into shared memory (LDGSTS): all rows of this
         // thread's column are in flight at once, at no register cost
         const TX *xc = x + c0 + col;
         const uint32_t dst0 = smem_u32(tile + col);
 #pragma unroll 8
-        for (int b = 0; b < bc; ++b)
+        for (int b = (kCompactW < kCompactThreads ? tid / kCompactW : 0); b < bc; b += kRowGroups)
             asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst0 + static_cast<uint32_t>(b * (kCompactW + 1) * sizeof(TX))),
                          "l"(xc + b * x_bstride), "n"(sizeof(TX))
                          : "memory");
