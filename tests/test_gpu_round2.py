@@ -816,3 +816,46 @@ def test_batch_offsets_beyond_2_31_elements(smm_lib, oracle, cuda):
             assert bool((y[:, n_dst:] == -5.0).all())                # padding of y untouched
     finally:
         smm_lib.smm_destroy(h)
+
+
+@pytest.mark.parametrize("negative", [False, True])
+def test_split_plan_short_rows_packed_long_rows_gathered(smm_lib, oracle, cuda, negative):
+    """Mostly short rows plus a few long ones: the short rows run in the packed staged kernel, the
+    long ones in a gather launch over a row list -- with positive weights (fast sums, 1e-12) and
+    with weights of both signs (reference order on both parts: bit-identical)."""
+    rng = np.random.default_rng(77 + negative)
+    n_src, n_dst, B = 8192, 5000, 19
+    counts = rng.integers(0, 9, size=n_dst)
+    long_rows = rng.choice(n_dst, size=60, replace=False)
+    counts[long_rows] = rng.integers(17, 120, size=60)
+    dst = np.repeat(np.arange(n_dst), counts)
+    src = np.clip((dst * n_src) // n_dst + rng.integers(-400, 400, size=dst.size), 0, n_src - 1)
+    w = rng.standard_normal(dst.size) if negative else rng.random(dst.size)
+    o = np.lexsort((src, dst))
+    src, dst, w = src[o] + 1, dst[o] + 1, w[o].reshape(-1, 1)
+    x = (280 + 20 * rng.standard_normal((B, n_src))).astype(np.float32)
+    x[rng.random(x.shape) < 0.02] = np.nan
+    imask = (rng.random(n_dst) > 0.1).astype(np.int32)
+    frac = rng.random(n_dst)
+    mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, imask, frac, 0.5, True)
+    h = _create(smm_lib, src, dst, w, n_src, n_dst)
+    try:
+        info = _info(smm_lib, h)
+        nnz_row = np.bincount(mat.dst, minlength=n_dst)
+        assert info["packed_rows"] == 1 and info["gather_rows"] == int((nnz_row > 16).sum()) > 40
+        assert info["summation_name"] == ("reference" if negative else "fast")
+        n0 = smm_lib.smm_launch_count()
+        y = _apply(smm_lib, h, x, n_dst, np.float64, True, 0.5, imask, frac)
+        assert smm_lib.smm_launch_count() - n0 == 2
+        if negative:
+            assert_identical(y, y_ref, "split plan, reference order")
+        else:
+            assert_parity(y, y_ref, RTOL_F64, "split plan")
+        yg = _apply(smm_lib, h, x, n_dst, np.float64, True, 0.5, imask, frac, kernel=2)      # whole operator gathered
+        assert_parity(yg, y_ref, RTOL_F64, "gather")
+        yr = _apply(smm_lib, h, x, n_dst, np.float64, True, 0.5, imask, frac, renormalize=0.3)
+        ref_r = oracle.apply_weights_renorm_np(x, mat, imask, frac, 0.5, True, 0.3)
+        assert np.array_equal(np.isnan(yr), np.isnan(ref_r))
+    finally:
+        smm_lib.smm_destroy(h)
