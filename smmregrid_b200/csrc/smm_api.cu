@@ -125,6 +125,7 @@ int upload_level(const HostCsr &csr, const HostPlan &plan, LevelDev &L)
         if ((rc = upload(&L.iplan, plan.iplan, L.device_bytes))) return rc;
         L.packed = plan.packed;
         L.reordered = plan.reordered;
+        L.ordlong = plan.ordlong;
         if (plan.packed) { if ((rc = upload(&L.rowmap, plan.rowslot, L.device_bytes))) return rc; }
         else if (!plan.rowmap.empty() && (rc = upload(&L.rowmap, plan.rowmap, L.device_bytes))) return rc;
         L.n_gather_rows = static_cast<int32_t>(plan.gather_rows.size());
@@ -212,12 +213,19 @@ int host_threads_all()
     return sched_getaffinity(0, sizeof(set), &set) == 0 ? std::max(1, CPU_COUNT(&set)) : 1;
 }
 
+int env_int_plan(const char *name, int dflt)
+{
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
 // Tile plans of all levels, one layout for the whole weight set so that a grouped launch runs a
 // single kernel.  Candidates, in order of preference:
 //   packed        every row has <= 16 links: a thread owns up to 4 rows;
 //   split         a few rows are longer (at most 1/8 of the rows, 40 % of the links: the fans of
 //                 cells around the grid poles of a tripolar ocean grid): the short rows are packed,
 //                 the long ones are listed for the gather kernel (HostPlan::gather_rows);
+//   ordered-long  (reference-order sums only) a thread per row, links in shared memory;
 //   lanes per row from the longest row.
 // A packed tile holds 4x the rows, so its footprint may not fit where the lane-per-row tile's
 // does: if any level's packed plan is unusable for that reason, all levels fall back to the next
@@ -241,14 +249,26 @@ void plan_levels(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, 
     }
     // levels are independent: a few host threads take them in turn (75 ocean levels: ~13 s -> ~1 s)
     const int nthreads = std::max(1, std::min({host_threads_all(), 16, static_cast<int>(csrs.size())}));
-    enum Mode { kSplit, kPacked, kLanes };
+    // reference-order sums for rows beyond the packed layout: a thread per row with the links in
+    // shared memory (ordered_kernel) when an image of K = longest row links x R rows x 12 bytes fits
+    // ~100 KB for some R in {256, 128, 64, 32}; else the lane-by-lane chain of staged_kernel<ORD>
+    int32_t ord_k = 0, ord_rows = 0;
+    if (ref_order && pc.cfg && !pc.packed && env_int_plan("SMM_ORDLONG", 1) != 0) {
+        for (const HostCsr &c : csrs) ord_k = std::max(ord_k, c.max_row_nnz);
+        for (int32_t r : {256, 128, 64, 32})
+            if (ord_rows == 0 && static_cast<int64_t>(ord_k) * r * 12 <= 100 * 1024) ord_rows = r;
+        if (const int forced = env_int_plan("SMM_ORD_ROWS", 0)) ord_rows = forced;
+    }
+    enum Mode { kSplit, kPacked, kOrdLong, kLanes };
     std::vector<Mode> modes;
     if (split) modes.push_back(kSplit);
     if (pc.packed) modes.push_back(kPacked);
+    if (ord_rows > 0) modes.push_back(kOrdLong);
     modes.push_back(kLanes);
     for (Mode mode : modes) {
-        const int32_t nct = mode == kLanes ? (ref_order ? 256 : default_consumer_threads(n_dst, pc.cfg ? pc.lpr : 0, sm_count))
-                                           : (ref_order ? 256 : default_consumer_threads(0, 1, sm_count));
+        const int32_t nct = mode == kOrdLong ? ord_rows
+                            : mode == kLanes ? (ref_order ? 256 : default_consumer_threads(n_dst, pc.cfg ? pc.lpr : 0, sm_count))
+                                             : (ref_order ? 256 : default_consumer_threads(0, 1, sm_count));
         std::atomic<size_t> next{0};
         std::atomic<bool> retry{false};
         auto work = [&]() {
@@ -261,6 +281,10 @@ void plan_levels(const std::vector<HostCsr> &csrs, int64_t n_dst, int sm_count, 
                     build_plan(csrs[i], -1, pc.kpl, nct, ref_order, plans[i], &srows);
                     plans[i].gather_rows = std::move(lrows);
                     if (!plans[i].ok) retry.store(true);           // any failure: the whole set takes the next layout
+                } else if (mode == kOrdLong) {
+                    build_plan(csrs[i], 1, ord_k, nct, true, plans[i]);
+                    plans[i].ordlong = plans[i].ok;
+                    if (!plans[i].ok && !csrs[i].col.empty()) retry.store(true);
                 } else {
                     build_plan(csrs[i], mode == kPacked ? -1 : pc.lpr, pc.kpl, nct, ref_order, plans[i]);
                     // only a footprint that is too large can be cured by smaller tiles
@@ -454,9 +478,13 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
     if (B == 0 || specs.empty()) return SMM_OK;
     const size_t sx = x_dtype == SMM_F32 ? 4 : 8;
     const bool ord = h->ref_order;
-    // shared memory a staged launch needs for `nstages` stages of one batch row each
-    auto staged_smem = [&](size_t max_segs, size_t max_elems, size_t nstages) {
-        return kSmemHeader + round_up(max_segs * sizeof(Seg), 128) + nstages * round_up(max_elems * sx, 128);
+    // shared memory a staged launch needs for `nstages` stages of one batch row each (`image` = the
+    // link image of ordered-long plans: kpl x nct x (8 + 4) bytes)
+    auto image_bytes = [](const LevelDev &L) -> size_t {
+        return L.ordlong ? round_up(static_cast<size_t>(L.kpl) * L.nct * 12, 128) : 0;
+    };
+    auto staged_smem = [&](size_t max_segs, size_t max_elems, size_t nstages, size_t image = 0) {
+        return kSmemHeader + round_up(max_segs * sizeof(Seg), 128) + image + nstages * round_up(max_elems * sx, 128);
     };
     std::vector<JobSpec> staged, gather, gather_lists;      // gather_lists: the long rows of split plans
     for (const JobSpec &s : specs) {
@@ -468,13 +496,13 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
             return fail(SMM_ERR_INVALID, "remap_area_min > 0 but dst_grid_frac was never set for level " +
                                              std::to_string(s.level));
         bool ok = L.staged && opt.kernel != SMM_KERNEL_GATHER;
-        // the renormalising extension is not implemented for packed-rows plans: gather kernel
-        ok = ok && !(L.packed && opt.renorm_min_valid >= 0.0);
+        // the renormalising extension is not implemented for packed-rows and ordered-long plans: gather kernel
+        ok = ok && !((L.packed || L.ordlong) && opt.renorm_min_valid >= 0.0);
         // TMA bulk copies need 16-byte aligned rows and lengths
         ok = ok && (reinterpret_cast<uintptr_t>(s.x) % 16 == 0) && ((xbs * sx) % 16 == 0) &&
              ((L.n_src * sx) % 16 == 0);
         // at least two stages must fit
-        ok = ok && staged_smem(L.max_segs, L.max_elems, 2) <= h->smem_optin;
+        ok = ok && staged_smem(L.max_segs, L.max_elems, 2, image_bytes(L)) <= h->smem_optin;
         if (!ok && opt.kernel == SMM_KERNEL_STAGED)
             return fail(SMM_ERR_INVALID, "staged kernel forced but unavailable for level " +
                                              std::to_string(s.level) + ": " +
@@ -511,17 +539,23 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         int64_t tiles_total = 0;
         size_t max_segs = 0, max_elems = 0;
         int lpr = 0, kpl = 0, nct = 256;
-        bool packed = false;
+        bool packed = false, ordl = false;
+        size_t image = 0;
         for (; g1 < staged.size() && g1 - g0 < staged_per; ++g1) {
             const LevelDev &L = h->levels[staged[g1].level];
             const size_t ms = std::max<size_t>(max_segs, L.max_segs), me = std::max<size_t>(max_elems, L.max_elems);
-            if (g1 > g0 && staged_smem(ms, me, 2) > h->smem_optin) break;
+            if (g1 > g0 && staged_smem(ms, me, 2, image_bytes(L)) > h->smem_optin) break;
             max_segs = ms; max_elems = me;
             tiles_total += L.ntiles;
-            lpr = L.lpr; kpl = L.kpl; nct = L.nct; packed = L.packed;
+            lpr = L.lpr; kpl = L.kpl; nct = L.nct; packed = L.packed; ordl = L.ordlong;
+            image = image_bytes(L);
             a.n_src = L.n_src; a.n_dst = L.n_dst;
         }
-        const size_t stage_off = kSmemHeader + round_up(max_segs * sizeof(Seg), 128);
+        const size_t segs_off = kSmemHeader + round_up(max_segs * sizeof(Seg), 128);
+        const size_t stage_off = segs_off + image;
+        a.ord_k = kpl;
+        a.wimg_off = static_cast<uint32_t>(segs_off);
+        a.oimg_off = static_cast<uint32_t>(segs_off + static_cast<size_t>(kpl) * nct * 8);
         const size_t row_bytes = std::max<size_t>(128, round_up(max_elems * sx, 128));
         // stage several batch rows together (up to 8, ~56 KB per stage) so that the per-stage
         // barrier and loop overhead of the consumers is amortised: C3 2156 -> 2671 GB/s, C2 5565 -> 6111
@@ -533,14 +567,22 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
             nb_rows = static_cast<int>(std::min<size_t>(nb_rows, std::max<size_t>(1, budget / (4 * row_bytes))));
         }
         nb_rows = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>({nb_rows, 8, B})));
+        if (ordl) {     // ordered kernel: one CTA per SM, batch rows chained in pairs: an even number of rows
+                        // per stage, as many as leave three stages
+            nb_rows = (B >= 2 && stage_off + 4 * row_bytes <= h->smem_optin) ? 2 : 1;
+            while (nb_rows >= 2 && nb_rows + 2 <= 8 && nb_rows + 2 <= B &&
+                   stage_off + 3 * static_cast<size_t>(nb_rows + 2) * row_bytes <= h->smem_optin)
+                nb_rows += 2;
+        }
         const size_t stage_bytes = row_bytes * nb_rows;
         int64_t chunk = 0;             // batch rows per work item: whole stages
         const double row_bytes_hbm = static_cast<double>(g1 - g0) *
                                      (static_cast<double>(a.n_src) * sx + static_cast<double>(a.n_dst) * (y_dtype == SMM_F32 ? 4 : 8));
-        const int64_t nchunks = pick_chunks(B, tiles_total, static_cast<int64_t>(h->sm_count) * (nct == 256 ? 2 : 1),
-                                            row_bytes_hbm, nct == 256 ? 2.5 : 4.0, nb_rows, chunk);
+        const int ctas_per_sm = (!ordl && nct == 256) ? 2 : 1;
+        const int64_t nchunks = pick_chunks(B, tiles_total, static_cast<int64_t>(h->sm_count) * ctas_per_sm,
+                                            row_bytes_hbm, ordl ? 6.0 : (nct == 256 ? 2.5 : 4.0), nb_rows, chunk);
         a.chunk = chunk; a.nchunks = static_cast<int32_t>(nchunks);
-        size_t S = (nct == 256 && half > stage_off) ? (half - stage_off) / stage_bytes : 0;
+        size_t S = (!ordl && nct == 256 && half > stage_off) ? (half - stage_off) / stage_bytes : 0;
         if (S < 3) S = (h->smem_optin - stage_off) / stage_bytes;        // one CTA per SM
         S = std::min<size_t>(S, kMaxStages);
         S = std::min<size_t>(S, static_cast<size_t>(k_max_stages));
@@ -566,7 +608,8 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         g0 = g1;
         if (max_tiles == 0) continue;
         const dim3 grid(static_cast<unsigned>(max_tiles), static_cast<unsigned>(nchunks), static_cast<unsigned>(jb.njobs));
-        const int rc = SMM_DTYPE_DISPATCH(launch_staged_t, h->device, lpr, kpl, nct, packed, ord, grid, smem, st, jb, a);
+        const int rc = ordl ? SMM_DTYPE_DISPATCH(launch_ordered_t, h->device, nct, grid, smem, st, jb, a)
+                            : SMM_DTYPE_DISPATCH(launch_staged_t, h->device, lpr, kpl, nct, packed, ord, grid, smem, st, jb, a);
         if (rc) return rc;
     }
 

@@ -90,6 +90,8 @@ struct ApplyArgs {
     double remap_area_min;
     double renorm_min_valid;  // < 0: reference semantics (fill 1e20); >= 0: opt-in renormalising mode
     uint32_t debug_flags; // bit 0: stream only (profiling aid: consumers skip the arithmetic)
+    int32_t ord_k;        // ordered_kernel: links per row of the shared-memory image (= the plan's links per lane)
+    uint32_t wimg_off, oimg_off;   // ordered_kernel: byte offsets of the weight / offset images in shared memory
 };
 
 }  // namespace smm

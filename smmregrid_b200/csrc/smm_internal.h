@@ -42,6 +42,7 @@ struct LevelDev {
     uint16_t *iplan = nullptr;
     int32_t *rowmap = nullptr;          // tile slot -> row (re-ordered plans) | packed plans: the rowslot table
     bool packed = false, reordered = false;
+    bool ordlong = false;               // reference-order plan for long rows: a thread per row, links in shared memory (ordered_kernel)
     int32_t *tcols = nullptr, *blk_ptr = nullptr, *rcol = nullptr;   // compact (two-pass) plan of gather levels
     int32_t compact_blocks = 0;
     int32_t *gather_rows = nullptr;     // split plans: the long rows the gather kernel serves next to the staged launch
@@ -65,6 +66,11 @@ template <typename TX, typename TY>
 int launch_staged_t(int dev, int lpr, int kpl, int nct, bool packed, bool ord, dim3 grid, size_t smem,
                     cudaStream_t st, const JobBatch &jb, const ApplyArgs &a);
 
+// ordered_kernel<TX, TY, rows_per_tile> (reference-order sums, a thread per row, links in shared memory)
+template <typename TX, typename TY>
+int launch_ordered_t(int dev, int rows_per_tile, dim3 grid, size_t smem, cudaStream_t st, const JobBatch &jb,
+                     const ApplyArgs &a);
+
 // gather_kernel<TX, TY, lpr, ord>
 template <typename TX, typename TY>
 int launch_gather_t(int lpr, bool ord, dim3 grid, cudaStream_t st, const JobBatch &jb, const ApplyArgs &a);
@@ -79,6 +85,8 @@ int launch_compact_t(int dev, const LevelDev &L, const JobSpec &sp, void *xt, in
                                                 const JobBatch &, const ApplyArgs &);                      \
     EXTERN template int launch_gather_t<TX, TY>(int, bool, dim3, cudaStream_t, const JobBatch &,           \
                                                 const ApplyArgs &);                                        \
+    EXTERN template int launch_ordered_t<TX, TY>(int, int, dim3, size_t, cudaStream_t, const JobBatch &,   \
+                                                 const ApplyArgs &);                                       \
     EXTERN template int launch_compact_t<TX, TY>(int, const LevelDev &, const JobSpec &, void *, int64_t,  \
                                                  int64_t, int64_t, double, cudaStream_t);
 

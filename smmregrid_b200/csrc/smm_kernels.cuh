@@ -395,6 +395,50 @@ constexpr int kProducerRegs = 40;
 // consumers grow to 104 (4 consumer warps x 104 + 1 producer warp x 40 per sub-partition <= 512).
 __host__ __device__ constexpr int consumer_regs(int nct) { return nct == 512 ? SMM_CONSUMER_REGS_512 : 96; }
 
+// per-tile segment table in bytes: {dst offset in the stage, length, source offset in the row}
+struct SegB { uint32_t dst, len; uint64_t src; };
+
+// TMA producer warp `p` of `nwarps`: for every stage of up to NB consecutive batch rows of the work
+// item, wait for the stage to be free, then stream the tile's footprint with 1-D bulk copies
+// (producer p issues copies p, p + active, ... one per lane); completion is counted in bytes on
+// the stage's `full` mbarrier.
+template <typename TX>
+__device__ __forceinline__ void produce_stages(const LevelJob &job, const ApplyArgs &a, const TileDesc &td,
+                                               const SegB *ssegs, uint32_t full_addr, uint32_t empty_addr,
+                                               uint32_t stages_addr, int p, int nwarps, int lane, int64_t b0, int64_t b1)
+{
+    // small footprints need fewer issuing warps (<= 3 copies each); the others retire at once
+    const int per_stage = td.nseg * a.rows_per_stage;
+    const int active = per_stage >= 3 * nwarps ? nwarps : (per_stage + 2) / 3 > 0 ? (per_stage + 2) / 3 : 1;
+    if (p >= active) return;
+    const uint64_t policy = l2_evict_first_policy();
+    const char *xbase = static_cast<const char *>(job.x);
+    const uint32_t tile_bytes = static_cast<uint32_t>(td.elems) * sizeof(TX);
+    const int NB = a.rows_per_stage;
+    const int S = a.nstages;
+    const int64_t xrow_stride = a.x_bstride * static_cast<int64_t>(sizeof(TX));
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t g = b0; g < b1; g += NB) {          // one stage = up to NB consecutive batch rows
+        const int nb = (g + NB <= b1) ? NB : static_cast<int>(b1 - g);
+        mbar_wait(empty_addr + 8 * s, ph ^ 1u);
+        const uint32_t fb = full_addr + 8 * s;
+        // the phase cannot complete before this arrive, so copies of the other producers that
+        // land earlier only drive the transaction count transiently negative
+        if (p == 0 && lane == 0) mbar_arrive_expect_tx(fb, tile_bytes * static_cast<uint32_t>(nb));
+        const char *xg = xbase + g * xrow_stride;
+        const uint32_t sbase = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
+        const int ncopies = nb * td.nseg;
+        for (int i = p + active * lane; i < ncopies; i += 32 * active) {
+            const int n = i / td.nseg;
+            const SegB e = ssegs[i - n * td.nseg];
+            tma_bulk_g2s(sbase + static_cast<uint32_t>(n) * a.row_bytes + e.dst, xg + n * xrow_stride + e.src, e.len,
+                         fb, policy);
+        }
+        if (++s == S) { s = 0; ph ^= 1u; }
+    }
+}
+
 // PACKED (LPR = 1, KPL = 16): a thread owns up to four short destination rows, one per 4-link
 // sub-row (a longer row continues into the next sub-rows); job.rowmap then holds
 // [ntiles][4][NCT] = destination row of a sub-row, -1 empty, -2 continuation of the previous one.
@@ -422,8 +466,6 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
     const int64_t b1 = (b0 + a.chunk < a.B) ? b0 + a.chunk : a.B;
     const TileDesc td = job.tiles[tile];
 
-    // per-tile segment table in bytes: {dst offset in the stage, length, source offset in the row}
-    struct SegB { uint32_t dst, len; uint64_t src; };
     SegB *ssegs = reinterpret_cast<SegB *>(smem + kSmemHeader);
     const uint32_t smem_addr = pin_reg(smem_u32(smem));
     const uint32_t full_addr = smem_addr, empty_addr = smem_addr + 8 * kMaxStages;
@@ -448,36 +490,8 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
         // ---------------- producer warps: TMA bulk copies of the footprint, one stage per batch
         // row; producer p issues segments p, p + 4, ... (one per lane)
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kProducerRegs));
-        const int p = warp - kConsumerWarps;
-        // small footprints need fewer issuing warps (<= 3 copies each); the others retire at once
-        const int per_stage = td.nseg * a.rows_per_stage;
-        const int active = per_stage >= 3 * kProducerWarps ? kProducerWarps : (per_stage + 2) / 3 > 0 ? (per_stage + 2) / 3 : 1;
-        if (p >= active) return;
-        const uint64_t policy = l2_evict_first_policy();
-        const char *xbase = static_cast<const char *>(job.x);
-        const uint32_t tile_bytes = static_cast<uint32_t>(td.elems) * sizeof(TX);
-        const int NB = a.rows_per_stage;
-        const int64_t xrow_stride = a.x_bstride * static_cast<int64_t>(sizeof(TX));
-        int s = 0;
-        uint32_t ph = 0;
-        for (int64_t g = b0; g < b1; g += NB) {          // one stage = up to NB consecutive batch rows
-            const int nb = (g + NB <= b1) ? NB : static_cast<int>(b1 - g);
-            mbar_wait(empty_addr + 8 * s, ph ^ 1u);
-            const uint32_t fb = full_addr + 8 * s;
-            // the phase cannot complete before this arrive, so copies of the other producers that
-            // land earlier only drive the transaction count transiently negative
-            if (p == 0 && lane == 0) mbar_arrive_expect_tx(fb, tile_bytes * static_cast<uint32_t>(nb));
-            const char *xg = xbase + g * xrow_stride;
-            const uint32_t sbase = stages_addr + static_cast<uint32_t>(s) * a.stage_bytes;
-            const int ncopies = nb * td.nseg;
-            for (int i = p + active * lane; i < ncopies; i += 32 * active) {
-                const int n = i / td.nseg;
-                const SegB e = ssegs[i - n * td.nseg];
-                tma_bulk_g2s(sbase + static_cast<uint32_t>(n) * a.row_bytes + e.dst, xg + n * xrow_stride + e.src, e.len,
-                             fb, policy);
-            }
-            if (++s == S) { s = 0; ph ^= 1u; }
-        }
+        produce_stages<TX>(job, a, td, ssegs, full_addr, empty_addr, stages_addr, warp - kConsumerWarps, kProducerWarps,
+                           lane, b0, b1);
     } else {
         // ---------------- consumer warps: links live in registers for the whole batch loop
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(consumer_regs(NCT)));
@@ -657,6 +671,163 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
             }
             if (++s == S) { s = 0; ph ^= 1u; }
         }
+    }
+}
+
+// ------------------------------------------------------------------ ordered (reference-order) kernel, long rows
+//
+// Reference-order sums for rows too long for a thread's registers.  The staged kernel spreads such
+// a row over LPR lanes, and a chain that has to visit the lanes one after the other leaves all but
+// one lane in LPR idle.  Here a THREAD owns a row (R rows per tile = R consumer threads) and walks
+// its links -- the k-th link of thread t at [k][t] of an image of (float64 weight, stage byte offset)
+// pairs the CTA keeps in SHARED memory for the whole batch loop (conflict-free: the lanes of a warp
+// read consecutive words) -- adding the products one by one in ascending source order.  Two batch
+// rows are chained at a time (the image is read once for both; two independent dependency chains).
+// Same producers, stages and epilogue as staged_kernel; plan = the lane-per-row register image with
+// LPR = 1 and KPL = K = the longest row (ApplyArgs::ord_k), slot k = the row's k-th link.
+
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+template <typename TX, int R, bool kFill>
+__device__ __forceinline__ void chain_pair(uint32_t wa, uint32_t oa, int K, uint32_t s0, uint32_t s1, double &a0, double &a1)
+{
+    a0 = 0.0;
+    a1 = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k, wa += R * 8, oa += R * 4) {
+        const double w = lds_f64(wa);
+        const uint32_t o = lds_u32(oa);
+        TX v0 = lds<TX>(s0 + o);
+        TX v1 = lds<TX>(s1 + o);
+        if (kFill) { v0 = fill_invalid(v0); v1 = fill_invalid(v1); }
+        a0 = __dadd_rn(a0, __dmul_rn(static_cast<double>(v0), w));
+        a1 = __dadd_rn(a1, __dmul_rn(static_cast<double>(v1), w));
+    }
+}
+
+constexpr int kOrderedProducerWarps = 4;
+
+template <typename TX, typename TY, int R>
+__global__ void __launch_bounds__(R + 32 * kOrderedProducerWarps, 1)
+ordered_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ ApplyArgs a)
+{
+    constexpr int kThreads = R + 32 * kOrderedProducerWarps;
+    constexpr int kConsumerWarps = R / 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    const LevelJob &job = jb.jobs[blockIdx.z];
+    const int tile = blockIdx.x;
+    const int chunk = blockIdx.y;
+    if (tile >= job.nblocks) return;
+    const int64_t b0 = static_cast<int64_t>(chunk) * a.chunk;
+    const int64_t b1 = (b0 + a.chunk < a.B) ? b0 + a.chunk : a.B;
+    const TileDesc td = job.tiles[tile];
+    const int K = a.ord_k;
+
+    SegB *ssegs = reinterpret_cast<SegB *>(smem + kSmemHeader);
+    double *wimg = reinterpret_cast<double *>(smem + a.wimg_off);
+    uint32_t *oimg = reinterpret_cast<uint32_t *>(smem + a.oimg_off);
+    const uint32_t smem_addr = smem_u32(smem);
+    const uint32_t full_addr = smem_addr, empty_addr = smem_addr + 8 * kMaxStages;
+    const uint32_t stages_addr = smem_addr + a.stage_off;
+    const int S = a.nstages;
+
+    for (int i = tid; i < td.nseg; i += kThreads) {
+        const Seg sg = job.segs[td.seg0 + i];
+        ssegs[i] = SegB{sg.dst * static_cast<uint32_t>(sizeof(TX)), sg.len * static_cast<uint32_t>(sizeof(TX)),
+                        static_cast<uint64_t>(sg.src) * sizeof(TX)};
+    }
+    {   // the tile's link image: [K][R] weights and stage byte offsets
+        const size_t ibase = static_cast<size_t>(tile) * K * R;
+        for (int i = tid; i < K * R; i += kThreads) {
+            wimg[i] = __ldg(job.wplan + ibase + i);
+            // absolute shared address of the link in stage 0, row 0: what is added per batch row is a
+            // pure function of the stage and row counters and stays in a uniform register
+            oimg[i] = stages_addr + static_cast<uint32_t>(__ldg(job.iplan + ibase + i)) * static_cast<uint32_t>(sizeof(TX));
+        }
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(full_addr + 8 * s, 1);
+            mbar_init(empty_addr + 8 * s, kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp >= kConsumerWarps) {
+        produce_stages<TX>(job, a, td, ssegs, full_addr, empty_addr, stages_addr, warp - kConsumerWarps,
+                           kOrderedProducerWarps, lane, b0, b1);
+        return;
+    }
+    // (the role branch above is warp-uniform, which the compiler cannot see: an ALIGNED barrier
+    // among the consumer warps tells it that they are converged, so that the batch loop's control
+    // and the stage offsets may live in uniform registers -- staged_kernel gets the same effect from
+    // its setmaxnreg.sync.aligned)
+    asm volatile("barrier.sync.aligned 1, %0;" ::"n"(R) : "memory");
+    const bool valid = tid < td.nrows;
+    const int row = (job.rowmap && valid) ? job.rowmap[td.row0 + tid] : td.row0 + tid;
+    bool dead = false;
+    if (valid) {
+        if (job.masked && job.imask[row] == 0) dead = true;
+        if (a.remap_area_min > 0.0 && job.frac[row] < a.remap_area_min) dead = true;
+    }
+    TY *yp = static_cast<TY *>(job.y) + row + b0 * a.y_bstride;
+    const uint32_t wa = smem_u32(wimg) + static_cast<uint32_t>(tid) * 8u;
+    const uint32_t oa = smem_u32(oimg) + static_cast<uint32_t>(tid) * 4u;
+    const int NB = a.rows_per_stage;
+    bool prefer_fill = false;      // warp-uniform: the previous pair needed the 1e20 fill
+    uint32_t n_done = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t g = b0; g < b1; g += NB) {
+        const int nb = (g + NB <= b1) ? NB : static_cast<int>(b1 - g);
+        mbar_wait(full_addr + 8 * s, ph);
+        uint32_t sb = static_cast<uint32_t>(s) * a.stage_bytes;          // uniform: LDS [R_link + UR_sb]
+#pragma unroll 1
+        for (int n = 0; n < nb; n += 2, sb += 2 * a.row_bytes) {
+            const bool two = n + 1 < nb;
+            const uint32_t s1 = two ? sb + a.row_bytes : sb;
+            double a0, a1;
+            // fast path on raw values; a non-finite sum (some source was NaN / inf) makes the warp
+            // redo the pair with the 1e20 fill, and stay on the filled chain while that keeps happening
+            const bool probe = !prefer_fill || (n_done & 15u) == 0;
+            ++n_done;
+            if (!probe) {
+                chain_pair<TX, R, true>(wa, oa, K, sb, s1, a0, a1);
+            } else {
+                prefer_fill = false;
+                chain_pair<TX, R, false>(wa, oa, K, sb, s1, a0, a1);
+                if (__any_sync(0xffffffffu, not_finite(a0) || not_finite(a1))) {
+                    chain_pair<TX, R, true>(wa, oa, K, sb, s1, a0, a1);
+                    prefer_fill = true;
+                }
+            }
+            if (n + 2 >= nb) {                           // last rows read: the stage may be refilled
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_addr + 8 * s);
+            }
+            if (valid) {
+                store_y(yp, finish<TY, true>(a0, dead, []() { return 0.0; }));
+                if (two) store_y(yp + a.y_bstride, finish<TY, true>(a1, dead, []() { return 0.0; }));
+            }
+            yp += (two ? 2 : 1) * a.y_bstride;
+        }
+        if (++s == S) { s = 0; ph ^= 1u; }
     }
 }
 

@@ -40,6 +40,29 @@ int launch_staged_t(int dev, int lpr, int kpl, int nct, bool packed, bool ord, d
 }
 
 template <typename TX, typename TY>
+int launch_ordered_t(int dev, int rows_per_tile, dim3 grid, size_t smem, cudaStream_t st, const JobBatch &jb,
+                     const ApplyArgs &a)
+{
+#define SMM_ORD_CASE(R_)                                                                          \
+    if (rows_per_tile == R_) {                                                                    \
+        auto kfn = ordered_kernel<TX, TY, R_>;                                                    \
+        static std::atomic<size_t> optin[kMaxDevices];                                            \
+        if (dev < 0 || dev >= kMaxDevices || optin[dev].load(std::memory_order_relaxed) < smem) { \
+            CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                          static_cast<int>(smem)));                               \
+            if (dev >= 0 && dev < kMaxDevices) optin[dev].store(smem, std::memory_order_relaxed); \
+        }                                                                                         \
+        kfn<<<grid, R_ + 32 * kOrderedProducerWarps, smem, st>>>(jb, a);                          \
+        CUDA_TRY(cudaGetLastError());                                                             \
+        smm_count_launches(1);                                                                    \
+        return 0;                                                                                 \
+    }
+    SMM_ORD_CASE(32) SMM_ORD_CASE(64) SMM_ORD_CASE(128) SMM_ORD_CASE(256)
+#undef SMM_ORD_CASE
+    return smm_fail(1, "no ordered kernel for this tile height");
+}
+
+template <typename TX, typename TY>
 int launch_gather_t(int lpr, bool ord, dim3 grid, cudaStream_t st, const JobBatch &jb, const ApplyArgs &a)
 {
     if (ord) gather_kernel<TX, TY, 1, true><<<grid, kGatherThreads, 0, st>>>(jb, a);

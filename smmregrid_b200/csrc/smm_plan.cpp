@@ -143,7 +143,7 @@ static void build_plan_rows(const HostCsr &csr, int32_t force_lpr, int32_t force
 {
     plan = HostPlan{};
     plan.ref_order = ref_order;
-    if (nct != 256 && nct != 512) nct = 256;
+    if (nct < 32 || nct > 512 || nct % 32 != 0) nct = 256;
     int32_t lpr = force_lpr, kpl = force_kpl;
     int32_t max_row = csr.max_row_nnz;
     if (order) {

@@ -47,6 +47,8 @@ struct HostPlan {
     bool reordered = false;        // rows were tiled in mean-source-address order
     bool packed = false;           // packed-rows plan: one thread owns up to 4 short rows (4 link slots each)
     bool ref_order = false;        // links placed for reference-order summation (lane l, slot k = link l*kpl + k)
+    bool ordlong = false;          // ref_order plan with one lane per row and kpl = the longest row, nct = rows per
+                                   // tile (32..256): the image lives in shared memory (ordered_kernel)
     int64_t nrows = 0;             // destination rows this plan covers (n_dst unless it is one part of a split plan)
     // Split plans: operators whose rows are mostly short (<= 16 links) with a few long ones (the
     // fan of cells around a grid pole of a tripolar ocean grid) tile the short rows with the

@@ -20,7 +20,7 @@ namespace smm {
 
 namespace {
 
-constexpr char kMagic[8] = {'S', 'M', 'M', 'P', 'L', 'A', 'N', '4'};
+constexpr char kMagic[8] = {'S', 'M', 'M', 'P', 'L', 'A', 'N', '5'};
 
 // 4 interleaved 64-bit multiply-xorshift lanes over 8-byte words (a few GB/s on one core)
 struct Hasher {
@@ -110,7 +110,7 @@ template <typename IO> void io_plan(IO &io, HostPlan &p)
 {
     io.pod(p.ok); io.str(p.why);
     io.pod(p.lpr); io.pod(p.kpl); io.pod(p.rows_per_tile); io.pod(p.nct);
-    io.pod(p.reordered); io.pod(p.packed); io.pod(p.ref_order);
+    io.pod(p.reordered); io.pod(p.packed); io.pod(p.ref_order); io.pod(p.ordlong);
     io.pod(p.max_tile_segments); io.pod(p.max_tile_elems); io.pod(p.sum_tile_elems); io.pod(p.sum_tile_cols);
     io.vec(p.tiles); io.vec(p.segs); io.vec(p.rowmap); io.vec(p.rowslot); io.vec(p.wplan); io.vec(p.iplan);
     io.pod(p.nrows);

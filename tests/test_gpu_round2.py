@@ -84,10 +84,14 @@ def _apply(lib, h, x, n_dst, ydtype=np.float64, masked=False, amin=0.0, imask=No
 # ------------------------------------------------------------------ reference-order summation
 
 @pytest.mark.parametrize("xdt", [np.float32, np.float64])
-@pytest.mark.parametrize("nnz_per_row", [2, 7, 12, 16, 30, 60, 120, 200, 400])
-def test_mixed_sign_operator_is_bit_identical(smm_lib, oracle, cuda, xdt, nnz_per_row):
+@pytest.mark.parametrize("nnz_per_row,ordlong", [(2, 1), (7, 1), (12, 1), (16, 1), (30, 1), (60, 1), (120, 1), (200, 1),
+                                                 (400, 1), (30, 0), (60, 0), (120, 0), (200, 0), (400, 0)])
+def test_mixed_sign_operator_is_bit_identical(smm_lib, oracle, cuda, monkeypatch, xdt, nnz_per_row, ordlong):
     """Weights of both signs (sums cancel): the operator is planned for the reference's summation
-    order and every kernel family returns the oracle's float64 values bit for bit."""
+    order and every kernel family returns the oracle's float64 values bit for bit: packed rows
+    (<= 16 links), a thread per row with the links in shared memory (ordered_kernel, while the image
+    fits) and -- `ordlong` = 0 or very long rows -- the lane-by-lane chain of staged_kernel<ORD>."""
+    monkeypatch.setenv("SMM_ORDLONG", str(ordlong))
     rng = np.random.default_rng(300 + nnz_per_row)
     n_src, n_dst, B = 4096, 700, 37
     counts = rng.integers(0, nnz_per_row + 1, size=n_dst)
@@ -110,6 +114,9 @@ def test_mixed_sign_operator_is_bit_identical(smm_lib, oracle, cuda, xdt, nnz_pe
         info = _info(smm_lib, h)
         assert info["summation_name"] == "reference" and info["kernel_name"] == "staged"
         assert info["packed_rows"] == (1 if nnz_per_row <= 16 else 0)
+        if nnz_per_row > 16:
+            thread_per_row = ordlong == 1 and nnz_per_row <= 266           # 32 rows x K links x 12 bytes <= 100 KB
+            assert (info["lanes_per_row"] == 1 and info["links_per_lane"] == info["max_row_nnz"]) == thread_per_row
         for kernel in (0, 2, 3):
             y = _apply(smm_lib, h, x, n_dst, np.float64, True, 0.5, imask, frac, kernel)
             assert_identical(y, y_ref, f"nnz{nnz_per_row} kernel{kernel}")
@@ -151,7 +158,8 @@ def test_forced_reference_summation_for_sign_changing_data(smm_lib, oracle, cuda
     y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False)
     h = _create(smm_lib, w, summation="reference")
     try:
-        assert _info(smm_lib, h)["summation_name"] == "reference" and _info(smm_lib, h)["lanes_per_row"] == 8
+        info = _info(smm_lib, h)          # a thread per row, ~110 links each, in shared memory
+        assert info["summation_name"] == "reference" and info["lanes_per_row"] == 1 and info["links_per_lane"] >= 100
         for kernel in (0, 2):
             assert_identical(_apply(smm_lib, h, x, n_dst, kernel=kernel), y_ref, f"reference order, kernel {kernel}")
     finally:
