@@ -867,3 +867,33 @@ def test_split_plan_short_rows_packed_long_rows_gathered(smm_lib, oracle, cuda, 
             assert_parity(yr, oracle.apply_weights_renorm_np(x, mat, imask, frac, 0.5, True, 0.3), 1e-12, "renorm")
     finally:
         smm_lib.smm_destroy(h)
+
+
+@pytest.mark.parametrize("ordlong", [1, 0])
+def test_reference_order_on_reordered_rows(smm_lib, oracle, cuda, monkeypatch, ordlong):
+    """Long rows of both signs whose destination order is scrambled: tiles of consecutive rows would
+    have footprints all over the source, so the plan tiles the rows re-ordered by mean source
+    address (row map) -- in the thread-per-row ordered kernel and in the lane-chained one alike,
+    bit-identical to the oracle."""
+    monkeypatch.setenv("SMM_ORDLONG", str(ordlong))
+    rng = np.random.default_rng(91)
+    n_src, n_dst, B, k = 200000, 3000, 11, 40
+    perm = rng.permutation(n_dst)
+    dst = np.repeat(np.arange(n_dst), k)
+    centre = (perm[dst].astype(np.int64) * n_src) // n_dst
+    src = np.clip(centre + rng.integers(-300, 300, size=dst.size), 0, n_src - 1)
+    w = rng.standard_normal(dst.size)
+    o = np.lexsort((src, dst))
+    src, dst, w = src[o] + 1, dst[o] + 1, w[o].reshape(-1, 1)
+    x = (50 * rng.standard_normal((B, n_src))).astype(np.float32)
+    x[rng.random(x.shape) < 0.01] = np.nan
+    mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False)
+    h = _create(smm_lib, src, dst, w, n_src, n_dst)
+    try:
+        info = _info(smm_lib, h)
+        assert info["kernel_name"] == "staged" and info["rows_reordered"] == 1 and info["summation_name"] == "reference"
+        assert (info["lanes_per_row"] == 1) == (ordlong == 1)
+        assert_identical(_apply(smm_lib, h, x, n_dst), y_ref, f"reordered rows, ordlong={ordlong}")
+    finally:
+        smm_lib.smm_destroy(h)
