@@ -897,3 +897,46 @@ def test_reference_order_on_reordered_rows(smm_lib, oracle, cuda, monkeypatch, o
         assert_identical(_apply(smm_lib, h, x, n_dst), y_ref, f"reordered rows, ordlong={ordlong}")
     finally:
         smm_lib.smm_destroy(h)
+
+
+def test_plan_cache_restores_every_plan_kind(smm_lib, oracle, cuda, tmp_path):
+    """The on-disk plan cache round-trips split plans (packed rows + row lists, per level) and
+    thread-per-row reference-order plans: a second Regridder built from the cache reports the same
+    plan and returns identical results."""
+    import torch
+    from smmregrid_b200 import Regridder, synth
+    from smmregrid_b200.weights import CdoWeights
+    cache = str(tmp_path / "plans")
+    # (1) tripolar 3-D weights: split plans
+    w = synth.config_weights("C3tri", 4)                         # 90 x 73 source, 18 levels -> r90x45
+    L, n_src, n_dst = 18, 90 * 73, 90 * 45
+    x = synth.synthetic_field((3, L, n_src), np.float32, seed=2)
+    outs, infos = [], []
+    for _ in range(2):
+        rg = Regridder(weights=w, remap_area_min=0.5, plan_cache_dir=cache)
+        infos.append([rg.weights_matrix.info(l) for l in range(L)])
+        outs.append(rg.regrid(x))
+    assert [i["plan_cache_hit"] for i in infos[0]] == [0] * L and [i["plan_cache_hit"] for i in infos[1]] == [1] * L
+    assert infos[0][0]["gather_rows"] > 0 and infos[0][0]["packed_rows"] == 1
+    strip = lambda i: {k: v for k, v in i.items() if k != "plan_cache_hit"}
+    assert [strip(i) for i in infos[0]] == [strip(i) for i in infos[1]]
+    assert_identical(outs[0], outs[1], "split plans from the cache")
+    # (2) long rows of both signs: thread-per-row reference-order plan
+    rng = np.random.default_rng(4)
+    n_src, n_dst, k = 6000, 800, 45
+    dst = np.repeat(np.arange(n_dst), k)
+    src = np.clip((dst * n_src) // n_dst + rng.integers(-200, 200, size=dst.size), 0, n_src - 1)
+    o = np.lexsort((src, dst))
+    w2 = CdoWeights({"src_address": (src[o] + 1).astype(np.int32), "dst_address": (dst[o] + 1).astype(np.int32),
+                     "remap_matrix": rng.standard_normal((dst.size, 1)), "src_grid_imask": np.ones(n_src, np.int32),
+                     "dst_grid_imask": np.ones(n_dst, np.int32), "dst_grid_frac": np.ones(n_dst),
+                     "src_grid_dims": np.array([n_src], np.int32), "dst_grid_dims": np.array([n_dst], np.int32)},
+                    attrs={"source_grid": "a", "dest_grid": "b"})
+    x2 = rng.standard_normal((7, n_src)).astype(np.float32)
+    mat = oracle.compute_weights_matrix_c(w2["src_address"], w2["dst_address"], w2["remap_matrix"], n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x2, mat, None, None, 0.0, False)
+    for hit in (0, 1):
+        rg = Regridder(weights=w2, remap_area_min=0.0, plan_cache_dir=cache)
+        info = rg.weights_matrix.info()
+        assert info["plan_cache_hit"] == hit and info["summation_name"] == "reference" and info["lanes_per_row"] == 1
+        assert_identical(rg.regrid(torch.from_numpy(x2).cuda()).cpu().numpy(), y_ref, f"ordered plan, cache hit {hit}")
