@@ -68,8 +68,8 @@ int launch_staged_t(int dev, int lpr, int kpl, int nct, bool packed, bool ord, d
 
 // ordered_kernel<TX, TY, rows_per_tile> (reference-order sums, a thread per row, links in shared memory)
 template <typename TX, typename TY>
-int launch_ordered_t(int dev, int rows_per_tile, dim3 grid, size_t smem, cudaStream_t st, const JobBatch &jb,
-                     const ApplyArgs &a);
+int launch_ordered_t(int dev, int rows_per_tile, int threads_per_row, dim3 grid, size_t smem, cudaStream_t st,
+                     const JobBatch &jb, const ApplyArgs &a);
 
 // gather_kernel<TX, TY, lpr, ord>
 template <typename TX, typename TY>
@@ -85,8 +85,8 @@ int launch_compact_t(int dev, const LevelDev &L, const JobSpec &sp, void *xt, in
                                                 const JobBatch &, const ApplyArgs &);                      \
     EXTERN template int launch_gather_t<TX, TY>(int, bool, dim3, cudaStream_t, const JobBatch &,           \
                                                 const ApplyArgs &);                                        \
-    EXTERN template int launch_ordered_t<TX, TY>(int, int, dim3, size_t, cudaStream_t, const JobBatch &,   \
-                                                 const ApplyArgs &);                                       \
+    EXTERN template int launch_ordered_t<TX, TY>(int, int, int, dim3, size_t, cudaStream_t,                \
+                                                 const JobBatch &, const ApplyArgs &);                     \
     EXTERN template int launch_compact_t<TX, TY>(int, const LevelDev &, const JobSpec &, void *, int64_t,  \
                                                  int64_t, int64_t, double, cudaStream_t);
 

@@ -725,14 +725,85 @@ __device__ __forceinline__ void chain_pair(uint32_t wa, uint32_t oa, int K, uint
     }
 }
 
+template <typename TX, int R, bool kFill>
+__device__ __forceinline__ double chain_one(uint32_t wa, uint32_t oa, int K, uint32_t s0)
+{
+    double acc = 0.0;
+#pragma unroll kOrdUnroll
+    for (int k = 0; k < K; ++k, wa += R * 8, oa += R * 4) {
+        const double w = lds_f64(wa);
+        TX v = lds<TX>(s0 + lds_u32(oa));
+        if (kFill) v = fill_invalid(v);
+        acc = __dadd_rn(acc, __dmul_rn(static_cast<double>(v), w));
+    }
+    return acc;
+}
+
 constexpr int kOrderedProducerWarps = 4;
 
-template <typename TX, typename TY, int R>
-__global__ void __launch_bounds__(R + 32 * kOrderedProducerWarps, 1)
+// Consumer loop of ordered_kernel with TWO threads per row: thread group HALF (0 | 1; R threads
+// each, whole warps) chains batch row HALF of every pair of staged rows, so twice as many warps
+// share the latency of the dependent offset -> value -> convert -> multiply -> add pipeline.  A
+// separate instantiation per HALF keeps the stage offset of "my" row a uniform register.
+template <typename TX, typename TY, int R, int HALF>
+__device__ __forceinline__ void ordered_consume_half(const LevelJob &job, const ApplyArgs &a, const TileDesc &td,
+                                                     uint32_t wimg_addr, uint32_t oimg_addr, uint32_t full_addr,
+                                                     uint32_t empty_addr, int t, int lane, int64_t b0, int64_t b1)
+{
+    asm volatile("barrier.sync.aligned %0, %1;" ::"n"(1 + HALF), "n"(R) : "memory");      // convergence, see ordered_kernel
+    const bool valid = t < td.nrows;
+    const int row = (job.rowmap && valid) ? job.rowmap[td.row0 + t] : td.row0 + t;
+    bool dead = false;
+    if (valid) {
+        if (job.masked && job.imask[row] == 0) dead = true;
+        if (a.remap_area_min > 0.0 && job.frac[row] < a.remap_area_min) dead = true;
+    }
+    TY *yp = static_cast<TY *>(job.y) + row + (b0 + HALF) * a.y_bstride;
+    const uint32_t wa = wimg_addr + static_cast<uint32_t>(t) * 8u;
+    const uint32_t oa = oimg_addr + static_cast<uint32_t>(t) * 4u;
+    const int NB = a.rows_per_stage, S = a.nstages, K = a.ord_k;
+    bool prefer_fill = false;
+    uint32_t n_done = 0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t g = b0; g < b1; g += NB) {
+        const int nb = (g + NB <= b1) ? NB : static_cast<int>(b1 - g);
+        mbar_wait(full_addr + 8 * s, ph);
+        uint32_t sb = static_cast<uint32_t>(s) * a.stage_bytes + HALF * a.row_bytes;      // uniform
+#pragma unroll 1
+        for (int n = HALF; n < nb + HALF; n += 2, sb += 2 * a.row_bytes, yp += 2 * a.y_bstride) {
+            const bool mine = n < nb;                        // (an odd last pair has no row for HALF 1)
+            double acc = 0.0;
+            if (mine) {
+                const bool probe = !prefer_fill || (n_done & 15u) == 0;
+                ++n_done;
+                if (!probe) {
+                    acc = chain_one<TX, R, true>(wa, oa, K, sb);
+                } else {
+                    prefer_fill = false;
+                    acc = chain_one<TX, R, false>(wa, oa, K, sb);
+                    if (__any_sync(0xffffffffu, not_finite(acc))) {
+                        acc = chain_one<TX, R, true>(wa, oa, K, sb);
+                        prefer_fill = true;
+                    }
+                }
+            }
+            if (n + 2 >= nb + HALF) {                        // this group's last row of the stage is read
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_addr + 8 * s);
+            }
+            if (mine && valid) store_y(yp, finish<TY, true>(acc, dead, []() { return 0.0; }));
+        }
+        if (++s == S) { s = 0; ph ^= 1u; }
+    }
+}
+
+template <typename TX, typename TY, int R, int TPR = 1>     // TPR = threads per row (1: a thread chains both rows of a pair)
+__global__ void __launch_bounds__(R * TPR + 32 * kOrderedProducerWarps, 1)
 ordered_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ ApplyArgs a)
 {
-    constexpr int kThreads = R + 32 * kOrderedProducerWarps;
-    constexpr int kConsumerWarps = R / 32;
+    constexpr int kThreads = R * TPR + 32 * kOrderedProducerWarps;
+    constexpr int kConsumerWarps = R * TPR / 32;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -781,6 +852,15 @@ ordered_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Appl
     if (warp >= kConsumerWarps) {
         produce_stages<TX>(job, a, td, ssegs, full_addr, empty_addr, stages_addr, warp - kConsumerWarps,
                            kOrderedProducerWarps, lane, b0, b1);
+        return;
+    }
+    if constexpr (TPR == 2) {
+        if (tid < R)
+            ordered_consume_half<TX, TY, R, 0>(job, a, td, smem_u32(wimg), smem_u32(oimg), full_addr, empty_addr, tid,
+                                               lane, b0, b1);
+        else
+            ordered_consume_half<TX, TY, R, 1>(job, a, td, smem_u32(wimg), smem_u32(oimg), full_addr, empty_addr,
+                                               tid - R, lane, b0, b1);
         return;
     }
     // (the role branch above is warp-uniform, which the compiler cannot see: an ALIGNED barrier

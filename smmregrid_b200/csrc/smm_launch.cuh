@@ -40,25 +40,27 @@ int launch_staged_t(int dev, int lpr, int kpl, int nct, bool packed, bool ord, d
 }
 
 template <typename TX, typename TY>
-int launch_ordered_t(int dev, int rows_per_tile, dim3 grid, size_t smem, cudaStream_t st, const JobBatch &jb,
-                     const ApplyArgs &a)
+int launch_ordered_t(int dev, int rows_per_tile, int threads_per_row, dim3 grid, size_t smem, cudaStream_t st,
+                     const JobBatch &jb, const ApplyArgs &a)
 {
-#define SMM_ORD_CASE(R_)                                                                          \
-    if (rows_per_tile == R_) {                                                                    \
-        auto kfn = ordered_kernel<TX, TY, R_>;                                                    \
+#define SMM_ORD_CASE_T(R_, T_)                                                                    \
+    if (rows_per_tile == R_ && threads_per_row == T_) {                                           \
+        auto kfn = ordered_kernel<TX, TY, R_, T_>;                                                \
         static std::atomic<size_t> optin[kMaxDevices];                                            \
         if (dev < 0 || dev >= kMaxDevices || optin[dev].load(std::memory_order_relaxed) < smem) { \
             CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                           static_cast<int>(smem)));                               \
             if (dev >= 0 && dev < kMaxDevices) optin[dev].store(smem, std::memory_order_relaxed); \
         }                                                                                         \
-        kfn<<<grid, R_ + 32 * kOrderedProducerWarps, smem, st>>>(jb, a);                          \
+        kfn<<<grid, R_ * T_ + 32 * kOrderedProducerWarps, smem, st>>>(jb, a);                     \
         CUDA_TRY(cudaGetLastError());                                                             \
         smm_count_launches(1);                                                                    \
         return 0;                                                                                 \
     }
+#define SMM_ORD_CASE(R_) SMM_ORD_CASE_T(R_, 1) SMM_ORD_CASE_T(R_, 2)
     SMM_ORD_CASE(32) SMM_ORD_CASE(64) SMM_ORD_CASE(128) SMM_ORD_CASE(256)
 #undef SMM_ORD_CASE
+#undef SMM_ORD_CASE_T
     return smm_fail(1, "no ordered kernel for this tile height");
 }
 
