@@ -608,9 +608,10 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
         g0 = g1;
         if (max_tiles == 0) continue;
         const dim3 grid(static_cast<unsigned>(max_tiles), static_cast<unsigned>(nchunks), static_cast<unsigned>(jb.njobs));
-        // two threads per row (one per batch row of a pair) whenever pairs are staged: twice the warps
-        static const int k_ord_tpr = env_int("SMM_ORD_TPR", 2);
-        const int tpr = (ordl && nb_rows >= 2 && k_ord_tpr == 2) ? 2 : 1;
+        // two threads per row (one per batch row of a pair) while that leaves at most 8 consumer warps:
+        // C4 (64 rows per tile) 3060 -> 3989 GB/s, C2 (256 rows: 16 warps re-reading the image) 4368 -> 3518
+        static const int k_ord_tpr = env_int("SMM_ORD_TPR", 0);
+        const int tpr = (ordl && nb_rows >= 2 && (k_ord_tpr == 2 || (k_ord_tpr == 0 && nct <= 128))) ? 2 : 1;
         const int rc = ordl ? SMM_DTYPE_DISPATCH(launch_ordered_t, h->device, nct, tpr, grid, smem, st, jb, a)
                             : SMM_DTYPE_DISPATCH(launch_staged_t, h->device, lpr, kpl, nct, packed, ord, grid, smem, st, jb, a);
         if (rc) return rc;

@@ -930,6 +930,7 @@ def test_plan_cache_restores_every_plan_kind(smm_lib, oracle, cuda, tmp_path):
     w2 = CdoWeights({"src_address": (src[o] + 1).astype(np.int32), "dst_address": (dst[o] + 1).astype(np.int32),
                      "remap_matrix": rng.standard_normal((dst.size, 1)), "src_grid_imask": np.ones(n_src, np.int32),
                      "dst_grid_imask": np.ones(n_dst, np.int32), "dst_grid_frac": np.ones(n_dst),
+                     "dst_grid_masked": np.asarray(False),        # (a mask-sum over weights of both signs would mask half the cells)
                      "src_grid_dims": np.array([n_src], np.int32), "dst_grid_dims": np.array([n_dst], np.int32)},
                     attrs={"source_grid": "a", "dest_grid": "b"})
     x2 = rng.standard_normal((7, n_src)).astype(np.float32)
