@@ -95,7 +95,10 @@ typedef struct smm_info {
     int32_t n_levels;            /* 1 for a 2-D operator                                  */
     int32_t kernel;              /* SMM_KERNEL_* chosen for this level                    */
     int32_t lanes_per_row;       /* staged plan: lanes sharing one destination row        */
-    int32_t links_per_lane;      /* staged plan: register-resident links per lane         */
+    int32_t links_per_lane;      /* staged plan: register-resident links per lane; thread- */
+                                 /* per-row reference-order plans (lanes_per_row = 1,      */
+                                 /* more than 16 links): the longest row, kept in shared   */
+                                 /* memory                                                 */
     int32_t rows_per_tile;       /* staged plan: destination rows per tile                */
     int32_t n_tiles;
     int32_t max_row_nnz;
