@@ -150,6 +150,13 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append((time.perf_counter(), line.strip()))
 
+    def wait_first(self, timeout):
+        """Block until the first sample has arrived, so the timed region is certain to be covered."""
+        t_end = time.perf_counter() + timeout
+        while self.proc and not self.lines and time.perf_counter() < t_end:
+            time.sleep(0.02)
+        time.sleep(0.05)
+
     def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -417,7 +424,7 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.12)
+        sampler.wait_first(5.0)         # nvidia-smi can take a second to come up on a cold box
     launches0 = lib.smm_launch_count()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize(dev)
