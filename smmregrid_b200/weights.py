@@ -72,9 +72,9 @@ class CdoWeights:
           may be ``num_links`` or ``numLinks`` (CDO >= 2.2.0, ``weights.py:13``); for 3-D weights
           the level dimension is the one ``link_length`` is defined on and its coordinate variable
           gives the level values used by the nearest-level rule (``regrid.py:386-395``);
-        * netCDF-4 / HDF5 (what ``cdo`` writes by default with ``-f nc4``) needs ``h5py`` or
-          ``netCDF4``; without them convert once with ``cdo -f nc copy`` / ``ncks -3`` (or open
-          the file with xarray where that is installed and pass the Dataset).
+        * netCDF-4 / HDF5 (what ``cdo -f nc4`` writes and what the reference's ``engine="netcdf4"``
+          reads) through the package's own reader :mod:`smmregrid_b200.nc4` (deflate / shuffle /
+          chunked storage, dimension scales); no ``h5py`` or ``netCDF4`` is needed.
         """
         if path.endswith(".npz"):
             with np.load(path, allow_pickle=False) as z:
@@ -103,25 +103,12 @@ class CdoWeights:
 
     @classmethod
     def _from_hdf5(cls, path, mask_dim):
-        try:
-            import h5py
-        except ImportError as e:
-            raise ImportError(
-                f"{path} is a netCDF-4/HDF5 file and neither h5py nor netCDF4 is installed: convert it "
-                "once with `cdo -f nc copy in.nc out.nc` or `ncks -3 in.nc out.nc`, or open it with "
-                "xarray and pass the Dataset") from e
-        variables, dims = {}, {}
-        with h5py.File(path, "r") as f:
-            for k, v in f.items():
-                if not isinstance(v, h5py.Dataset):
-                    continue
-                is_scale = v.attrs.get("CLASS", b"") == b"DIMENSION_SCALE"
-                if is_scale and str(v.attrs.get("NAME", b"")).find("This is a netCDF dimension but not a netCDF variable") >= 0:
-                    continue                        # a bare dimension, no data
-                variables[k] = np.array(v[...])
-                dims[k] = tuple(d.label or (d.keys()[0] if len(d) else "") for d in v.dims) if not is_scale else (k,)
-            attrs = {k: (v.decode() if isinstance(v, bytes) else v) for k, v in f.attrs.items()
-                     if not k.startswith("_")}
+        from . import nc4                           # the package's own reader: no h5py / netCDF4 needed
+        with nc4.File(path) as f:
+            variables = {k: np.array(v[...]) for k, v in f.variables.items()
+                         if v.dtype is not None and v.dtype.kind in "fiu"}
+            dims = {k: tuple(v.dims) for k, v in f.variables.items() if k in variables}
+            attrs = dict(f.attrs)
         return cls._from_named(variables, dims, attrs, mask_dim)
 
     @classmethod

@@ -216,6 +216,40 @@ def real_data_case():
     print("tas_healpix2.npz:", tas.shape, tas.dtype, float(tas.min()), float(tas.max()))
 
 
+def netcdf4_cases():
+    """netCDF-4 (HDF5) data files of the reference's test suite, for the package's own reader
+    (smmregrid_b200/nc4.py; the image has neither netCDF4 nor h5py):
+
+    * the two smallest files travel as they are (tests/golden/data/healpix_0.nc, regional.nc:
+      written by the netCDF library through CDO / NCO -- superblock 2, version-2 object headers,
+      dense attributes, chunked + deflated + shuffled variables);
+    * ua-ipsl.nc (4 MB: eastward wind on 19 pressure levels, 143 x 144 lat-lon with points at the
+      poles, 1e20 under the orography: REAL level-dependent masks) is cut to one time step and its
+      six lowest levels, values untouched: tests/golden/ua_ipsl.npz;
+    * regional.nc was cut by `cdo sellonlatbox` from r360x180.nc: the reader must return the
+      same bits from both files (checked here, where both are readable)."""
+    import shutil
+    sys.path.insert(0, os.path.join(HERE, "..", ".."))
+    from smmregrid_b200 import nc4
+    data = "/root/reference/tests/data/"
+    os.makedirs(os.path.join(HERE, "data"), exist_ok=True)
+    for name in ("healpix_0.nc", "regional.nc"):
+        shutil.copyfile(data + name, os.path.join(HERE, "data", name))
+        os.chmod(os.path.join(HERE, "data", name), 0o644)
+    with nc4.File(data + "r360x180.nc") as g, nc4.File(data + "regional.nc") as r:
+        la, lo = g.variables["lat"][...], g.variables["lon"][...]
+        i0 = int(np.where(la == r.variables["lat"][0])[0][0])
+        j0 = int(np.where(lo == r.variables["lon"][0])[0][0])
+        assert np.array_equal(g.variables["pr"][...][0, i0:i0 + 90, j0:j0 + 61], r.variables["pr"][...][0])
+    with nc4.File(data + "ua-ipsl.nc") as f:
+        ua = f.variables["ua"]
+        assert ua.dims == ("time", "plev", "lat", "lon")
+        np.savez_compressed(os.path.join(HERE, "ua_ipsl.npz"), ua=ua[...][0, :6], plev=f.variables["plev"][:6],
+                            lat=f.variables["lat"][...], lon=f.variables["lon"][...],
+                            fill=np.float32(ua.attrs["_FillValue"]))
+        print("ua_ipsl.npz:", ua[...][0, :6].shape, [(int((ua[...][0, l] == 1e20).sum())) for l in range(6)])
+
+
 def _coord_record(da, key):
     c = da.coords[key]
     return {"dims": list(c.dims), "values": np.asarray(c.data), "attrs": dict(c.attrs)}
@@ -290,3 +324,5 @@ if __name__ == "__main__":
         real_data_case()
     if which in ("all", "dressing"):
         dressing_cases()
+    if which in ("all", "netcdf4"):
+        netcdf4_cases()

@@ -563,12 +563,87 @@ def test_weights_from_files(smm_lib, oracle, cuda, tmp_path):
     w3.save_npz(npz)
     back = CdoWeights.from_file(npz)
     assert back.mask_dim == "depth_full" and np.array_equal(back.levels, lev_values)
-    # a netCDF-4 / HDF5 file is recognised and reported (no h5py in this image)
-    bad = str(tmp_path / "w4.nc")
+    # netCDF-4 / HDF5 (what the reference's engine="netcdf4" reads): the package's own reader, 2-D and 3-D
+    import h5mini
+    path4 = str(tmp_path / "w4.nc")
+    h5mini.write_weights(path4, w)
+    rg4 = Regridder(weights=path4, remap_area_min=0.5)
+    assert rg4.weights.attrs["source_grid"] == "r36x18"
+    assert_parity(rg4.regrid(x).reshape(5, n_dst), y_ref, RTOL_F64, "netCDF-4 weights")
+    path43 = str(tmp_path / "w4_3d.nc")
+    h5mini.write_weights(path43, w3)
+    rg43 = Regridder(weights=path43, remap_area_min=0.5)
+    assert rg43.mask_dim == "depth_full" and np.array_equal(rg43.weights.levels, lev_values)
+    assert_parity(rg43.regrid(x3, levels=[1000.0, 10.0]).reshape(3, 2, n_dst), y_ref3, RTOL_F64, "3-D netCDF-4 weights")
+    # a damaged HDF5 file is reported
+    bad = str(tmp_path / "bad.nc")
     with open(bad, "wb") as f:
         f.write(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
-    with pytest.raises((ImportError, OSError)):
+    with pytest.raises(OSError):
         CdoWeights.from_file(bad)
+
+
+def test_real_3d_field_with_level_dependent_masks(smm_lib, oracle, cuda):
+    """Eastward wind of the reference's tests/data/ua-ipsl.nc (one step, six lowest pressure levels,
+    143 x 144 with rows at the poles; read by smmregrid_b200.nc4, values untouched in
+    tests/golden/ua_ipsl.npz): 1e20 under the orography -> NaN as xarray decodes it, masks differ per
+    level.  Per-level conservative weights built from the REAL masks (what `cdo gencon` does level
+    by level, cdogenerate.py:217-263), regridded 3-D with the nearest-level rule, against the
+    oracle; then as a DataArray with `plev` as the vertical dimension."""
+    import refshim
+    from smmregrid_b200 import Regridder, synth
+    g = np.load(os.path.join(HERE, "golden", "ua_ipsl.npz"))
+    raw, plev = g["ua"], g["plev"].astype(np.float64)
+    ua = raw.copy()
+    ua[raw == g["fill"]] = np.nan
+    L, nlat, nlon = ua.shape
+    assert (L, nlat, nlon) == (6, 143, 144) and np.isnan(ua).sum(axis=(1, 2)).tolist() == [5721, 3003, 2091, 755, 55, 0]
+    masks = np.isfinite(ua).reshape(L, -1).astype(np.int32)
+    per = [synth.conservative_latlon(nlon, nlat, 90, 45, src_poles=True, src_mask=masks[l]) for l in range(L)]
+    w = synth._stack_levels(per, masks, L, 90 * 45, level_values=plev)
+    n_src, n_dst = nlat * nlon, 90 * 45
+    mats = oracle.compute_weights_matrix3d_np(w["src_address"], w["dst_address"], w["remap_matrix"],
+                                              w["link_length"], n_src, n_dst, builder=oracle.compute_weights_matrix_c)
+    im = np.stack([oracle.mask_tensordot_c(w["src_grid_imask"][l], mats[l])[0] for l in range(L)])
+    other = np.nan_to_num(ua[:, ::-1], nan=0.0) * np.float32(0.5)             # 2nd step: another field, same masks
+    x = np.stack([ua, np.where(np.isnan(ua), np.float32(np.nan), other)]).reshape(2, L, n_src)   # [time, plev, cell]
+    for amin in (0.0, 0.5, 0.9):
+        y_ref = oracle.regrid3d_np(x, 1, plev, plev, mats, im, w["dst_grid_frac"], oracle.check_mask_np(im), amin)
+        rg = Regridder(weights=w, vertical_dim="plev", remap_area_min=amin)
+        y = rg.regrid(x.reshape(2, L, nlat, nlon))
+        assert y.shape == (2, L, 45, 90)
+        assert_parity(y.reshape(2, L, n_dst), y_ref, RTOL_F64, f"ua-ipsl amin={amin}")
+    # masked area shrinks with height, the top level of the cut is complete, winds keep their range
+    nn = np.isnan(y[0]).sum(axis=(1, 2))
+    assert nn[0] > nn[1] > nn[2] > nn[3] >= nn[4] >= nn[5] == 0
+    assert np.nanmin(y[0]) >= np.nanmin(ua) - 1e-3 and np.nanmax(y[0]) <= np.nanmax(ua) + 1e-3
+    # the xarray route: dims by name, levels matched by value from the `plev` coordinate, a level subset
+    da = refshim.DataArray(x.reshape(2, L, nlat, nlon)[:, [4, 1]], dims=("time", "plev", "lat", "lon"),
+                           coords={"time": np.array([0.0, 1.0]), "plev": plev[[4, 1]], "lat": g["lat"], "lon": g["lon"]},
+                           name="ua", attrs={"units": "m s-1"})
+    out = Regridder(weights=w, vertical_dim="plev", remap_area_min=0.5).regrid(da)
+    y_ref = oracle.regrid3d_np(x[:, [4, 1]], 1, plev[[4, 1]], plev, mats, im, w["dst_grid_frac"],
+                               oracle.check_mask_np(im), 0.5)
+    assert out.dims == ("time", "plev", "lat", "lon") and out.name == "ua" and out.attrs["units"] == "m s-1"
+    assert np.array_equal(np.asarray(out.coords["plev"].data), plev[[4, 1]])
+    assert_parity(np.asarray(out.data).reshape(2, 2, n_dst), y_ref, RTOL_F64, "ua-ipsl DataArray")
+
+
+def test_real_netcdf4_healpix_levels(smm_lib, oracle, cuda):
+    """tests/golden/data/healpix_0.nc as the netCDF library wrote it (HDF5: chunked, deflated,
+    dense attributes) -> smmregrid_b200.nc4 -> 2-D weights applied to [time, level, cell] data
+    (the reference's healpix tests): 90 levels of real temperature on the 12 base pixels."""
+    from smmregrid_b200 import Regridder, nc4, synth
+    with nc4.File(os.path.join(HERE, "golden", "data", "healpix_0.nc")) as f:
+        ta = f.variables["ta"].decoded()
+        assert f.variables["ta"].dims == ("time", "level_full", "x") and ta.shape == (2, 90, 12)
+    w = synth.healpix_weights(1, 36, 18, 1)
+    mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], 12, 36 * 18)
+    y_ref = oracle.apply_weights_c(ta.reshape(180, 12), mat, None, None, 0.0, False)
+    y = Regridder(weights=w).regrid(ta)
+    assert y.shape == (2, 90, 18, 36)
+    assert_parity(y.reshape(180, 36 * 18), y_ref, RTOL_F64, "healpix_0")
+    assert 180.0 < y.min() and y.max() < 300.0
 
 
 # ------------------------------------------------------------------ xarray / dask front end
