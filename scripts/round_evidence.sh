@@ -16,7 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # for the two-pass compact path that is one launch of each of its kernels)
 for wl in C4 C2 C3 C3tri C5dis C5nn; do
   python bench.py --workload $wl $Q > gpurun_out/${tag}_plain_${wl}.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:'staged_kernel|compact|gather_kernel' -s 3 -c $([ $wl = C5dis ] && echo 2 || echo 1) -f \
+  ncu --set full --clock-control none --import-source on -k regex:'staged_kernel|compact|gather_kernel' -s 3 -c $( { [ $wl = C5dis ] || [ $wl = C5nn ]; } && echo 2 || echo 1) -f \
       -o gpurun_out/${tag}_${wl} python bench.py --workload $wl $Q > gpurun_out/${tag}_ncu_${wl}.log 2>&1
 done
 ls -la gpurun_out | tail -20

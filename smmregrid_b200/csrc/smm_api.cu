@@ -624,10 +624,11 @@ int launch_jobs(const smm_handle *h, const std::vector<JobSpec> &specs, int32_t 
             const LevelDev &L = h->levels[sp.level];
             // Cost per batch row in HBM-byte equivalents, calibrated on B200 (C5nn / C5dis, f32 and
             // f64): a random gather costs ~120 bytes (a 64-byte sector at about half the streaming
-            // rate); the two passes move the slab, the touched columns twice-ish and the links, at
-            // ~2/3 of the streaming rate.  Runs of fewer than 16 batch values are not worth it.
+            // rate); the two passes move the slab (at the streaming rate: TMA bulk copies), the
+            // touched columns twice-ish and the links (random 256-byte runs), together ~1.2x the
+            // bytes at the streaming rate.  Runs of fewer than 16 batch values are not worth it.
             const double gather_cost = static_cast<double>(L.nnz) * 120.0;
-            const double compact_cost = 1.5 * (static_cast<double>(L.n_src) + static_cast<double>(L.touched) +
+            const double compact_cost = 1.2 * (static_cast<double>(L.n_src) + static_cast<double>(L.touched) +
                                                static_cast<double>(L.nnz)) * static_cast<double>(sx);
             bool use = L.rcol && opt.renorm_min_valid < 0.0 && opt.kernel != SMM_KERNEL_GATHER;
             if (opt.kernel != SMM_KERNEL_COMPACT) use = use && B >= 16 && gather_cost > compact_cost;

@@ -1036,47 +1036,82 @@ constexpr int kCompactRows = 32;        // destination rows per pass-2 block
 
 // Pass 1.  Block i owns source columns [i*W, (i+1)*W) and the touched columns among them,
 // tcols[blk_ptr[i] .. blk_ptr[i+1]) (ascending; their rank in tcols is the row of XT).
+// The block's [bc][W] piece of the slab comes in as bc 1-D TMA bulk copies (one per batch row,
+// W * sizeof(TX) bytes each, all in flight at once, completion counted on one mbarrier) when the
+// rows are 16-byte aligned (`bulk`), else as 4-byte asynchronous element copies (LDGSTS).
+constexpr int kCompactStride = kCompactW + 4;       // tile row stride in elements: a multiple of 16 bytes
+
 template <typename TX>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_kernel(const TX *__restrict__ x, int64_t x_bstride, int64_t n_src, int bc,
-               const int32_t *__restrict__ tcols, const int32_t *__restrict__ blk_ptr, TX *__restrict__ xt)
+               const int32_t *__restrict__ tcols, const int32_t *__restrict__ blk_ptr, TX *__restrict__ xt,
+               int bulk)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    TX *tile = reinterpret_cast<TX *>(smem_raw);                 // [bc][W + 1]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ int16_t tcol_s[kCompactW];
+    static_assert(kCompactW <= 32768, "touched columns of a block are kept as 16-bit offsets");
+    TX *tile = reinterpret_cast<TX *>(smem_raw);                 // [bc][kCompactStride]
     const int t0 = blk_ptr[blockIdx.x], t1 = blk_ptr[blockIdx.x + 1];
     if (t0 == t1) return;                                        // nothing touched here: not read at all
     const int64_t c0 = static_cast<int64_t>(blockIdx.x) * kCompactW;
     const int w = static_cast<int>((n_src - c0 < kCompactW) ? n_src - c0 : kCompactW);
     const int tid = threadIdx.x;
-    // thread (col, row group): the threads of a warp copy 32 consecutive columns of one batch row
-    // (one 128-byte line per LDGSTS instruction); with fewer than 256 columns per block the
-    // remaining threads take every (256 / W)-th batch row
-    constexpr int kRowGroups = kCompactThreads / kCompactW > 0 ? kCompactThreads / kCompactW : 1;
-    for (int col = tid % kCompactW; col < w; col += kCompactThreads) {
-        // asynchronous element copies straight into shared memory (LDGSTS): all rows of this
-        // thread's column are in flight at once, at no register cost
-        const TX *xc = x + c0 + col;
-        const uint32_t dst0 = smem_u32(tile + col);
-#pragma unroll 8
-        for (int b = (kCompactW < kCompactThreads ? tid / kCompactW : 0); b < bc; b += kRowGroups)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst0 + static_cast<uint32_t>(b * (kCompactW + 1) * sizeof(TX))),
-                         "l"(xc + b * x_bstride), "n"(sizeof(TX))
-                         : "memory");
+    const bool use_bulk = bulk && (w * sizeof(TX)) % 16 == 0;    // block-uniform
+    const uint32_t bar_addr = smem_u32(&bar);
+    if (use_bulk) {
+        if (tid == 0) {
+            mbar_init(bar_addr, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid < 32) {
+            if (tid == 0) mbar_arrive_expect_tx(bar_addr, static_cast<uint32_t>(bc) * w * sizeof(TX));
+            const uint64_t pol = l2_evict_first_policy();
+            for (int b = tid; b < bc; b += 32)
+                tma_bulk_g2s(smem_u32(tile + b * kCompactStride), x + c0 + b * x_bstride,
+                             static_cast<uint32_t>(w * sizeof(TX)), bar_addr, pol);
+        }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
+    // the block's touched columns (at most W of them), fetched while the copies are in flight:
+    // the transposition below then depends on shared memory only
+    for (int i = tid; i < t1 - t0; i += kCompactThreads) tcol_s[i] = static_cast<int16_t>(tcols[t0 + i] - c0);
+    if (use_bulk) {
+        __syncthreads();
+        mbar_wait(bar_addr, 0);
+    } else {
+        // thread (col, row group): the threads of a warp copy 32 consecutive columns of one batch
+        // row (one 128-byte line per LDGSTS instruction); with fewer than 256 columns per block the
+        // remaining threads take every (256 / W)-th batch row
+        constexpr int kRowGroups = kCompactThreads / kCompactW > 0 ? kCompactThreads / kCompactW : 1;
+        for (int col = tid % kCompactW; col < w; col += kCompactThreads) {
+            const TX *xc = x + c0 + col;
+            const uint32_t dst0 = smem_u32(tile + col);
+#pragma unroll 8
+            for (int b = (kCompactW < kCompactThreads ? tid / kCompactW : 0); b < bc; b += kRowGroups)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst0 + static_cast<uint32_t>(b * kCompactStride * sizeof(TX))),
+                             "l"(xc + b * x_bstride), "n"(sizeof(TX))
+                             : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+    }
     const int warp = tid >> 5, lane = tid & 31;
     for (int t = t0 + warp; t < t1; t += kCompactThreads / 32) {
-        const int c = tcols[t] - static_cast<int>(c0);
+        const int c = tcol_s[t - t0];
         TX *dst = xt + static_cast<int64_t>(t) * kCompactBC;
-        if (lane < bc) dst[lane] = tile[lane * (kCompactW + 1) + c];
-        if (kCompactBC > 32 && lane + 32 < bc) dst[lane + 32] = tile[(lane + 32) * (kCompactW + 1) + c];
+        if (lane < bc) dst[lane] = tile[lane * kCompactStride + c];
+        if (kCompactBC > 32 && lane + 32 < bc) dst[lane + 32] = tile[(lane + 32) * kCompactStride + c];
     }
 }
 
 // Pass 2.  Block = 32 destination rows x bc batch rows; warp w takes rows w, w + 8, ...; lanes are
-// batch rows.  rcol[j] = rank of link j's source column in tcols.
+// batch rows.  rcol[j] = rank of link j's source column in tcols.  The block's row pointers and
+// its links (a contiguous piece of the CSR; up to kCompactLinks of them) are staged in shared
+// memory first, so that a row costs one round trip to memory (its XT runs) instead of three.
+constexpr int kCompactLinks = 1024;
+
 template <typename TX, typename TY>
 __global__ void __launch_bounds__(kCompactThreads)
 compact_apply_kernel(const TX *__restrict__ xt, int bc, const int32_t *__restrict__ rowptr,
@@ -1085,20 +1120,40 @@ compact_apply_kernel(const TX *__restrict__ xt, int bc, const int32_t *__restric
                      double remap_area_min, int64_t n_dst, TY *__restrict__ y, int64_t y_bstride)
 {
     __shared__ TY out[kCompactBC][kCompactRows + 1];
+    __shared__ double val_s[kCompactLinks];
+    __shared__ int32_t rcol_s[kCompactLinks];
+    __shared__ int32_t rp[kCompactRows + 1];
+    __shared__ uint8_t dead_s[kCompactRows];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t row0 = static_cast<int64_t>(blockIdx.x) * kCompactRows;
-    for (int rl = warp; rl < kCompactRows; rl += kCompactThreads / 32) {
-        const int64_t row = row0 + rl;
-        if (row >= n_dst) break;
+    const int nrows = static_cast<int>((n_dst - row0 < kCompactRows) ? n_dst - row0 : kCompactRows);
+    if (tid <= nrows) rp[tid] = rowptr[row0 + tid];
+    if (tid < nrows) {
         bool dead = false;
-        if (masked && imask[row] == 0) dead = true;
-        if (remap_area_min > 0.0 && frac[row] < remap_area_min) dead = true;
+        if (masked && imask[row0 + tid] == 0) dead = true;
+        if (remap_area_min > 0.0 && frac[row0 + tid] < remap_area_min) dead = true;
+        dead_s[tid] = dead;
+    }
+    __syncthreads();
+    const int jb0 = rp[0], nl = rp[nrows] - jb0;
+    const bool staged = nl <= kCompactLinks;                    // block-uniform
+    if (staged) {
+        for (int i = tid; i < nl; i += kCompactThreads) {
+            rcol_s[i] = __ldg(rcol + jb0 + i);
+            val_s[i] = __ldg(val + jb0 + i);
+        }
+        __syncthreads();
+    }
+    // generic pointers: shared memory when staged, else the CSR arrays themselves
+    const int32_t *rc = staged ? rcol_s - jb0 : rcol;
+    const double *vl = staged ? val_s - jb0 : val;
+    for (int rl = warp; rl < nrows; rl += kCompactThreads / 32) {
         double a0 = 0.0, a1 = 0.0;
-        const int j1 = rowptr[row + 1];
+        const int j1 = rp[rl + 1];
 #pragma unroll 4
-        for (int j = rowptr[row]; j < j1; ++j) {
-            const TX *src = xt + static_cast<int64_t>(__ldg(rcol + j)) * kCompactBC;
-            const double wj = __ldg(val + j);
+        for (int j = rp[rl]; j < j1; ++j) {
+            const TX *src = xt + static_cast<int64_t>(rc[j]) * kCompactBC;
+            const double wj = vl[j];
             const TX v0 = lane < bc ? fill_invalid(__ldg(src + lane)) : TX(0);
             const TX v1 = lane + 32 < bc ? fill_invalid(__ldg(src + lane + 32)) : TX(0);
             a0 = __dadd_rn(a0, __dmul_rn(static_cast<double>(v0), wj));      // reference order, no FMA
@@ -1106,11 +1161,11 @@ compact_apply_kernel(const TX *__restrict__ xt, int bc, const int32_t *__restric
         }
         if (a0 > 1e19) a0 = CUDART_NAN;                                       // regrid.py:570
         if (a1 > 1e19) a1 = CUDART_NAN;
+        const bool dead = dead_s[rl] != 0;
         out[lane][rl] = static_cast<TY>(dead ? CUDART_NAN : a0);
         if (kCompactBC > 32) out[(lane + 32) % kCompactBC][rl] = static_cast<TY>(dead ? CUDART_NAN : a1);
     }
     __syncthreads();
-    const int nrows = static_cast<int>((n_dst - row0 < kCompactRows) ? n_dst - row0 : kCompactRows);
     for (int b = warp; b < bc; b += kCompactThreads / 32)
         if (lane < nrows) y[b * y_bstride + row0 + lane] = out[b][lane];
 }

@@ -2,6 +2,7 @@
 // the four smm_inst_*.cu translation units only, each of which instantiates one (x, y) type pair.
 #pragma once
 #include <atomic>
+#include <cstdlib>
 
 #include "smm_internal.h"
 #include "smm_kernels.cuh"
@@ -83,7 +84,7 @@ int launch_compact_t(int dev, const LevelDev &L, const JobSpec &sp, void *xt_raw
                      int64_t ybs, double area_min, cudaStream_t st)
 {
     TX *xt = static_cast<TX *>(xt_raw);
-    const size_t smem = static_cast<size_t>(kCompactBC) * (kCompactW + 1) * sizeof(TX);
+    const size_t smem = static_cast<size_t>(kCompactBC) * kCompactStride * sizeof(TX);
     static std::atomic<bool> optin[kMaxDevices];
     if (dev < 0 || dev >= kMaxDevices || !optin[dev].load(std::memory_order_relaxed)) {
         CUDA_TRY(cudaFuncSetAttribute(compact_kernel<TX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -91,11 +92,19 @@ int launch_compact_t(int dev, const LevelDev &L, const JobSpec &sp, void *xt_raw
         if (dev >= 0 && dev < kMaxDevices) optin[dev].store(true, std::memory_order_relaxed);
     }
     const unsigned grid2 = static_cast<unsigned>((L.n_dst + kCompactRows - 1) / kCompactRows);
-    for (int64_t b0 = 0; b0 < B; b0 += kCompactBC) {
-        const int bc = static_cast<int>(B - b0 < kCompactBC ? B - b0 : kCompactBC);
+    // bulk (TMA) copies of the slab rows need 16-byte aligned row pieces; SMM_COMPACT_BULK=0 forces element copies
+    static const bool bulk_env = [] { const char *e = getenv("SMM_COMPACT_BULK"); return !(e && e[0] == '0'); }();
+    const int bulk = bulk_env && reinterpret_cast<uintptr_t>(sp.x) % 16 == 0 && (xbs * sizeof(TX)) % 16 == 0 &&
+                     (kCompactW * sizeof(TX)) % 16 == 0;
+    // 8-byte elements: half the batch rows per pass keeps the pass-1 tile at the size that lets three
+    // blocks share an SM (one block's transposition overlaps the others' copies)
+    static const int rows64 = [] { const char *e = getenv("SMM_COMPACT_F64_ROWS"); return e ? atoi(e) : 32; }();
+    const int step = (sizeof(TX) == 8 && bulk && rows64 > 0 && rows64 < kCompactBC) ? rows64 : kCompactBC;
+    for (int64_t b0 = 0; b0 < B; b0 += step) {
+        const int bc = static_cast<int>(B - b0 < step ? B - b0 : step);
         compact_kernel<TX><<<static_cast<unsigned>(L.compact_blocks), kCompactThreads,
-                             static_cast<size_t>(bc) * (kCompactW + 1) * sizeof(TX), st>>>(
-            static_cast<const TX *>(sp.x) + b0 * xbs, xbs, L.n_src, bc, L.tcols, L.blk_ptr, xt);
+                             static_cast<size_t>(bc) * kCompactStride * sizeof(TX), st>>>(
+            static_cast<const TX *>(sp.x) + b0 * xbs, xbs, L.n_src, bc, L.tcols, L.blk_ptr, xt, bulk);
         compact_apply_kernel<TX, TY><<<grid2, kCompactThreads, 0, st>>>(
             xt, bc, L.rowptr, L.rcol, L.val, L.imask, L.frac, sp.masked, area_min, L.n_dst,
             static_cast<TY *>(sp.y) + b0 * ybs, ybs);

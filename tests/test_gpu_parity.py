@@ -713,20 +713,22 @@ def test_compact_two_pass_path(smm_lib, oracle, cuda, xdt, ydt, B):
 
 
 def test_compact_path_is_chosen_for_dense_scattered_operators(smm_lib, oracle, cuda):
-    """C5dis-like (4 links per row, random source order): with >= 16 batch rows the apply takes
-    the two-pass path by itself; a sparse nn-like operator keeps the direct gathers."""
+    """Scattered sources (random source order): with >= 16 batch rows of float32 the apply takes the
+    two-pass path by itself -- C5dis-like (4 links per row) and, since its first pass moves the slab
+    with TMA bulk copies, nn-like operators too; float64 input doubles the slab the first pass has
+    to move, there a sparse nn-like operator keeps the direct gathers."""
     from smmregrid_b200 import synth
-    for cfg, expect_compact in (("C5dis", True), ("C5nn", False)):
+    for cfg, xdt, expect_compact in (("C5dis", np.float32, True), ("C5nn", np.float32, True), ("C5nn", np.float64, False)):
         w = synth.config_weights(cfg, 8)
         n_src, n_dst = w.sizes["src_grid_size"], w.sizes["dst_grid_size"]
-        x = synth.synthetic_field((40, n_src), np.float32, seed=3, nan_mode="random")
+        x = synth.synthetic_field((40, n_src), xdt, seed=3, nan_mode="random")
         mat = oracle.compute_weights_matrix_c(w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
         y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False, nthreads=4)
         h = _create(smm_lib, w["src_address"], w["dst_address"], w["remap_matrix"], n_src, n_dst)
         try:
             n0 = smm_lib.smm_launch_count()
             y = _apply(smm_lib, h, x, n_dst, np.float64, False, 0.0)
-            assert (smm_lib.smm_launch_count() - n0 == 2) == expect_compact, cfg
+            assert (smm_lib.smm_launch_count() - n0 >= 2) == expect_compact, (cfg, xdt)
             assert_parity(y, y_ref, RTOL_F64, cfg)
             n0 = smm_lib.smm_launch_count()
             y8 = _apply(smm_lib, h, np.ascontiguousarray(x[:8]), n_dst, np.float64, False, 0.0)   # few rows: direct gathers

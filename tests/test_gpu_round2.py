@@ -282,6 +282,39 @@ def test_c5_full_size_against_oracle(smm_lib, oracle, cuda, cfg, xdt):
         smm_lib.smm_destroy(h)
 
 
+@pytest.mark.parametrize("xdt", [np.float32, np.float64])
+def test_compact_first_pass_bulk_and_element_copies(smm_lib, oracle, cuda, xdt):
+    """Pass 1 of the two-pass path moves the slab rows with TMA bulk copies when they are 16-byte
+    aligned, with 4-byte element copies otherwise.  A padded leading dimension makes the rows
+    aligned while the last column block is 130 columns wide (not a multiple of 16 bytes in
+    float32): both copy flavours in one launch; then the same data from a base address that is
+    off by one element (element copies everywhere).  float64 rows go 32 per pass when copied in
+    bulk.  Bit-identical to the reference-order oracle either way."""
+    import torch
+    rng = np.random.default_rng(77)
+    n_src, ldx, n_dst, B = 400002, 400004, 3001, 70
+    src, dst, w = random_links(rng, n_src, n_dst, 3, dup_frac=0.05, sort=False, negative=True)
+    x = (280 + 20 * rng.standard_normal((B, n_src))).astype(xdt)
+    x[rng.random(x.shape) < 0.02] = np.nan
+    mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
+    y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False)
+    tdt = torch.float32 if xdt == np.float32 else torch.float64
+    flat = torch.full((B * ldx + 1,), float("nan"), dtype=tdt, device="cuda")
+    h = _create(smm_lib, src, dst, w, n_src, n_dst)
+    try:
+        for shift, rows_per_pass in ((0, 64 if xdt == np.float32 else 32), (1, 64)):
+            xd = flat[shift:shift + B * ldx].view(B, ldx)
+            xd.fill_(float("nan"))
+            xd[:, :n_src] = torch.from_numpy(x).cuda()
+            assert (xd.data_ptr() % 16 == 0) == (shift == 0)
+            n0 = smm_lib.smm_launch_count()
+            y = _apply(smm_lib, h, x, n_dst, np.float64, kernel=3, device_x=xd)
+            assert smm_lib.smm_launch_count() - n0 == 2 * ((B + rows_per_pass - 1) // rows_per_pass), shift
+            assert_identical(y, y_ref, f"compact, base shifted by {shift} element(s)")
+    finally:
+        smm_lib.smm_destroy(h)
+
+
 # ------------------------------------------------------------------ real data, curvilinear ocean
 
 @pytest.mark.parametrize("k", [1, 4])
@@ -589,7 +622,7 @@ def test_real_3d_field_with_level_dependent_masks(smm_lib, oracle, cuda):
     tests/golden/ua_ipsl.npz): 1e20 under the orography -> NaN as xarray decodes it, masks differ per
     level.  Per-level conservative weights built from the REAL masks (what `cdo gencon` does level
     by level, cdogenerate.py:217-263), regridded 3-D with the nearest-level rule, against the
-    oracle; then as a DataArray with `plev` as the vertical dimension."""
+    oracle; then as a DataArray whose `plev` dimension is found by name."""
     import refshim
     from smmregrid_b200 import Regridder, synth
     g = np.load(os.path.join(HERE, "golden", "ua_ipsl.npz"))
@@ -601,6 +634,7 @@ def test_real_3d_field_with_level_dependent_masks(smm_lib, oracle, cuda):
     masks = np.isfinite(ua).reshape(L, -1).astype(np.int32)
     per = [synth.conservative_latlon(nlon, nlat, 90, 45, src_poles=True, src_mask=masks[l]) for l in range(L)]
     w = synth._stack_levels(per, masks, L, 90 * 45, level_values=plev)
+    w.mask_dim = "plev"                      # the level dimension of weights generated from this file
     n_src, n_dst = nlat * nlon, 90 * 45
     mats = oracle.compute_weights_matrix3d_np(w["src_address"], w["dst_address"], w["remap_matrix"],
                                               w["link_length"], n_src, n_dst, builder=oracle.compute_weights_matrix_c)
@@ -609,7 +643,7 @@ def test_real_3d_field_with_level_dependent_masks(smm_lib, oracle, cuda):
     x = np.stack([ua, np.where(np.isnan(ua), np.float32(np.nan), other)]).reshape(2, L, n_src)   # [time, plev, cell]
     for amin in (0.0, 0.5, 0.9):
         y_ref = oracle.regrid3d_np(x, 1, plev, plev, mats, im, w["dst_grid_frac"], oracle.check_mask_np(im), amin)
-        rg = Regridder(weights=w, vertical_dim="plev", remap_area_min=amin)
+        rg = Regridder(weights=w, remap_area_min=amin)
         y = rg.regrid(x.reshape(2, L, nlat, nlon))
         assert y.shape == (2, L, 45, 90)
         assert_parity(y.reshape(2, L, n_dst), y_ref, RTOL_F64, f"ua-ipsl amin={amin}")
@@ -621,7 +655,7 @@ def test_real_3d_field_with_level_dependent_masks(smm_lib, oracle, cuda):
     da = refshim.DataArray(x.reshape(2, L, nlat, nlon)[:, [4, 1]], dims=("time", "plev", "lat", "lon"),
                            coords={"time": np.array([0.0, 1.0]), "plev": plev[[4, 1]], "lat": g["lat"], "lon": g["lon"]},
                            name="ua", attrs={"units": "m s-1"})
-    out = Regridder(weights=w, vertical_dim="plev", remap_area_min=0.5).regrid(da)
+    out = Regridder(weights=w, remap_area_min=0.5).regrid(da)
     y_ref = oracle.regrid3d_np(x[:, [4, 1]], 1, plev[[4, 1]], plev, mats, im, w["dst_grid_frac"],
                                oracle.check_mask_np(im), 0.5)
     assert out.dims == ("time", "plev", "lat", "lon") and out.name == "ua" and out.attrs["units"] == "m s-1"
