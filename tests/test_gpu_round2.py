@@ -294,10 +294,19 @@ def test_compact_first_pass_bulk_and_element_copies(smm_lib, oracle, cuda, xdt):
     rng = np.random.default_rng(77)
     n_src, ldx, n_dst, B = 400002, 400004, 3001, 70
     src, dst, w = random_links(rng, n_src, n_dst, 3, dup_frac=0.05, sort=False, negative=True)
+    # rows without links (alone, in pairs, a whole warp's share of a block, the last row) and a few long rows
+    empty = np.isin(dst, np.array([1, 6, 7, 32, 33, 34, 35, 36, 64, 95, n_dst]))
+    src, dst, w = src[~empty], dst[~empty], w[~empty]
+    # (rows 40 and 41 together exceed the links a pass-2 block stages in shared memory)
+    extra = rng.integers(1, n_src + 1, 1500).astype(src.dtype)
+    src = np.concatenate([src, extra])
+    dst = np.concatenate([dst, np.repeat(np.array([3, 40, 41], dst.dtype), 500)])
+    w = np.concatenate([w, rng.standard_normal((1500,) + w.shape[1:])])
     x = (280 + 20 * rng.standard_normal((B, n_src))).astype(xdt)
     x[rng.random(x.shape) < 0.02] = np.nan
     mat = oracle.compute_weights_matrix_c(src, dst, w, n_src, n_dst)
     y_ref = oracle.apply_weights_c(x, mat, None, None, 0.0, False)
+    assert np.all(y_ref[:, [0, 5, 6, 31, 35, n_dst - 1]] == 0.0)
     tdt = torch.float32 if xdt == np.float32 else torch.float64
     flat = torch.full((B * ldx + 1,), float("nan"), dtype=tdt, device="cuda")
     h = _create(smm_lib, src, dst, w, n_src, n_dst)
