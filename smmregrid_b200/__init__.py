@@ -7,7 +7,7 @@ from .util import detect_nan_variation_dims
 from .weights import (CdoWeights, WeightsMatrix, check_mask, compute_weights_matrix,
                       compute_weights_matrix3d, enable_operator_cache, mask_tensordot, mask_weights)
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 
 __all__ = [
     "Regridder", "regrid", "CdoWeights", "WeightsMatrix", "compute_weights_matrix",

@@ -161,8 +161,9 @@ def regrid_sharded(regridder, x, group=None, gather: bool = True, dst: Optional[
     """Regrid this rank's block of the leading (batch) axis of ``x`` and optionally gather.
 
     ``x`` is the FULL array on every rank (or a lazily sliceable object); only
-    ``x[start:stop]`` of this rank is touched.  2-D operators only (for 3-D weights shard the
-    time axis yourself and call ``Regridder.regrid`` on the block).
+    ``x[start:stop]`` of this rank is touched.  For 3-D weights this splits the leading (time)
+    axis with the whole operator on every rank; :class:`LevelShardedRegridder` gives each rank
+    only the operators of its own levels instead.
     """
     import torch.distributed as dist
 
@@ -179,6 +180,112 @@ def regrid_sharded(regridder, x, group=None, gather: bool = True, dst: Optional[
     if not isinstance(y_local, torch.Tensor):
         y_local = torch.from_numpy(y_local)
     return gather_to_host(y_local, B, group=group, dst=dst, via=via, out=out)
+
+
+class LevelShardedRegridder:
+    """3-D weights over the GPUs of one box ("partition (time x level) pairs so
+    each GPU holds only the matrices of its levels when L >= G, else split time within level").
+
+    * ``n_levels >= world``: rank r builds the operator of ITS contiguous block of levels only
+      (``CdoWeights.isel_levels``: operator construction and device memory shrink by the number
+      of ranks) and regrids those levels of every time step;
+    * fewer levels than ranks: every rank holds the whole operator and takes a block of the
+      leading (time) axis.
+
+    Either way there is no data-path collective; ``regrid`` optionally gathers the result on the
+    host (``gather_to_host``).  Construct it on every rank of the process group, after
+    ``torch.cuda.set_device``; keyword arguments go to :class:`Regridder`.
+    """
+
+    def __init__(self, weights, group=None, **regridder_kw):
+        import numpy as np
+        import torch.distributed as dist
+        from .regrid import Regridder
+        from .weights import CdoWeights
+        self.group = group
+        if dist.is_available() and dist.is_initialized():
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        else:
+            self.world, self.rank = 1, 0
+        w = CdoWeights.from_any(weights, mask_dim=regridder_kw.get("mask_dim"))
+        if not w.is3d:
+            raise ValueError("LevelShardedRegridder needs 3-D weights; use regrid_sharded for 2-D ones")
+        self.levels = w.levels
+        self.n_levels = w.n_levels
+        self.n_src = w.sizes["src_grid_size"]
+        self.src_grid_shape = tuple(int(n) for n in np.atleast_1d(w["src_grid_dims"])[::-1])
+        self.by_level = self.n_levels >= self.world
+        if self.by_level:
+            self.start, self.stop = batch_shard(self.n_levels, self.world, self.rank)
+            self.local = Regridder(weights=w.isel_levels(slice(self.start, self.stop)), **regridder_kw) \
+                if self.stop > self.start else None       # (ceil partition: the last ranks may have no level)
+        else:
+            self.start, self.stop = 0, self.n_levels
+            self.local = Regridder(weights=w, **regridder_kw)
+
+    def _n_kept(self, shape) -> int:
+        """Number of leading (non-horizontal) axes of the data (``Regridder._n_horizontal_axes``)."""
+        shape = tuple(int(n) for n in shape)
+        gs = self.src_grid_shape
+        if len(shape) > len(gs) and shape[-len(gs):] == gs:
+            return len(shape) - len(gs)
+        if len(shape) > 1 and shape[-1] == self.n_src:
+            return len(shape) - 1
+        raise KeyError('Dimensions mismatch')
+
+    def regrid(self, x, level_axis=None, gather: bool = True, dst: Optional[int] = 0, via: str = "nccl", out=None):
+        """``x``: the FULL ``[time..., level, (lat, lon | cell)]`` array on every rank (numpy / torch /
+        anything sliceable with basic indexing); only this rank's levels -- or time steps -- are
+        touched.  ``gather=False``: this rank's block (``[..., L_local, tgt...]``, ``None`` on a rank
+        without levels; or its time steps).  Otherwise the whole result as a host tensor on rank
+        ``dst`` (``None`` elsewhere; ``dst=None``: on every rank)."""
+        import numpy as np
+        import torch
+        if not self.by_level:
+            start, stop = batch_shard(x.shape[0], self.world, self.rank)
+            y_local = self.local.regrid3d(x[start:stop], level_axis=level_axis)
+            if not isinstance(y_local, torch.Tensor):
+                y_local = torch.from_numpy(np.asarray(y_local))
+            return y_local if not gather else \
+                gather_to_host(y_local, x.shape[0], group=self.group, dst=dst, via=via, out=out)
+        ndim = len(x.shape)
+        nkept = self._n_kept(x.shape)
+        la = nkept - 1 if level_axis is None else level_axis % ndim
+        if la >= nkept:
+            raise ValueError("level_axis must be one of the non-horizontal axes")
+        if x.shape[la] != self.n_levels:
+            raise ValueError(f"data has {x.shape[la]} levels, weights {self.n_levels}")
+        y_local = None
+        if self.local is not None:
+            sl = [slice(None)] * ndim
+            sl[la] = slice(self.start, self.stop)
+            y_local = self.local.regrid3d(x[tuple(sl)], level_axis=la, levels=self.levels[self.start:self.stop],
+                                          transpose=True)      # [kept without level..., L_local, tgt...]
+            if not isinstance(y_local, torch.Tensor):
+                y_local = torch.from_numpy(np.asarray(y_local))
+        if not gather:
+            return y_local
+        # the gather works on the leading axis: levels to the front, and back afterwards (a view)
+        y_local = self._level_block(y_local, nkept)
+        full = gather_to_host(y_local, self.n_levels, group=self.group, dst=dst, via=via, out=out)
+        return None if full is None else torch.movedim(full, 0, nkept - 1)
+
+    def _level_block(self, y_local, nkept):
+        """``[L_local, ...]`` contiguous block for the gather.  A rank without levels still takes
+        part: it learns the shape and dtype of one level's block from rank 0 (host-side metadata)."""
+        import torch
+        import torch.distributed as dist
+        if y_local is not None:
+            y_local = torch.movedim(y_local, nkept - 1, 0).contiguous()
+        if batch_shard(self.n_levels, self.world, self.world - 1)[1] > batch_shard(self.n_levels, self.world, self.world - 1)[0]:
+            return y_local                                 # every rank has levels: nothing to agree on
+        meta = [(tuple(y_local.shape[1:]), y_local.dtype, y_local.device.type) if self.rank == 0 else None]
+        dist.broadcast_object_list(meta, src=0, group=self.group)
+        if y_local is None:
+            shape, dtype, dev = meta[0]
+            device = torch.device("cuda", torch.cuda.current_device()) if dev == "cuda" else torch.device("cpu")
+            y_local = torch.empty((0,) + tuple(shape), dtype=dtype, device=device)
+        return y_local
 
 
 def bind_to_gpu_numa(device_index: int) -> Optional[int]:

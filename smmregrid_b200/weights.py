@@ -148,6 +148,30 @@ class CdoWeights:
         new.update({k: np.asarray(v) for k, v in kw.items()})
         return CdoWeights(new, self.attrs, self.mask_dim, self.levels)
 
+    _PER_LEVEL = ("src_address", "dst_address", "remap_matrix", "src_grid_imask", "dst_grid_imask",
+                  "dst_grid_frac", "dst_grid_masked", "link_length")
+
+    def isel_levels(self, sel) -> "CdoWeights":
+        """3-D weights restricted to some of their levels (what ``weights.isel({mask_dim: sel})``
+        gives on the reference's Dataset): the level slices of every per-level variable
+        (``cdogenerate.py:310-343``), link padding trimmed to the longest remaining level.
+        Used to give each GPU only the operators of its own levels."""
+        if not self.is3d:
+            raise ValueError("isel_levels needs 3-D weights (with link_length)")
+        L = self.n_levels
+        idx = np.atleast_1d(np.arange(L)[sel])
+        ll = self.vars["link_length"][idx]
+        nl_max = int(ll.max()) if ll.size else 0
+        new = {}
+        for k, v in self.vars.items():
+            if k in self._PER_LEVEL and v.ndim >= 1 and v.shape[0] == L and \
+                    (v.ndim >= 2 or k in ("link_length", "dst_grid_masked")):
+                v = v[idx]
+                if k in ("src_address", "dst_address", "remap_matrix"):
+                    v = v[:, :nl_max]
+            new[k] = v
+        return CdoWeights(new, self.attrs, self.mask_dim, self.levels[idx])
+
     @property
     def is3d(self) -> bool:
         return "link_length" in self.vars

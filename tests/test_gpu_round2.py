@@ -689,6 +689,43 @@ def test_real_netcdf4_healpix_levels(smm_lib, oracle, cuda):
     assert 180.0 < y.min() and y.max() < 300.0
 
 
+def test_level_partition_matches_whole_operator(smm_lib, oracle, cuda):
+    """SURVEY.md §8e for 3-D weights: a rank holds only the operators of its own levels.  The
+    operators built from `isel_levels` blocks (what LevelShardedRegridder gives each rank) regrid
+    their levels to the same values as the whole operator, and a single-process
+    LevelShardedRegridder equals the plain Regridder."""
+    import torch
+    from smmregrid_b200 import Regridder, synth
+    from smmregrid_b200.shard import LevelShardedRegridder, batch_shard
+    L = 7
+    w = synth.ocean3d_weights(72, 36, 24, 12, n_levels=L, seed=5, level_values=np.array([5., 15, 30, 60, 120, 250, 500]))
+    n_src, n_dst = 72 * 36, 24 * 12
+    x = synth.synthetic_field((4, L, 36, 72), np.float32, seed=4, nan_mode="random")
+    mats = oracle.compute_weights_matrix3d_np(w["src_address"], w["dst_address"], w["remap_matrix"], w["link_length"],
+                                              n_src, n_dst, builder=oracle.compute_weights_matrix_c)
+    im = np.stack([oracle.mask_tensordot_c(w["src_grid_imask"][l], mats[l])[0] for l in range(L)])
+    y_ref = oracle.regrid3d_np(x.reshape(4, L, n_src), 1, w.levels, w.levels, mats, im, w["dst_grid_frac"],
+                               oracle.check_mask_np(im), 0.5)
+    whole = Regridder(weights=w, remap_area_min=0.5).regrid(x)
+    assert_parity(whole.reshape(4, L, n_dst), y_ref, RTOL_F64, "whole operator")
+    for world in (2, 3, 4):
+        parts = []
+        for rank in range(world):
+            a, b = batch_shard(L, world, rank)
+            if b == a:
+                continue
+            rg = Regridder(weights=w.isel_levels(slice(a, b)), remap_area_min=0.5)
+            assert len(rg.weights_matrix) == b - a                 # operators of these levels only
+            parts.append(rg.regrid3d(x[:, a:b], levels=w.levels[a:b]))
+        y = np.concatenate(parts, axis=1)
+        assert y.shape == (4, L, 12, 24)
+        assert np.array_equal(y, whole, equal_nan=True), world
+    sh = LevelShardedRegridder(w, remap_area_min=0.5)
+    assert sh.by_level and (sh.start, sh.stop) == (0, L)
+    y = sh.regrid(torch.from_numpy(x).cuda())
+    assert np.array_equal(y.numpy(), whole, equal_nan=True)
+
+
 # ------------------------------------------------------------------ xarray / dask front end
 
 def _dressing(tag):
