@@ -1110,14 +1110,90 @@ compact_kernel(const TX *__restrict__ x, int64_t x_bstride, int64_t n_src, int b
 // batch rows.  rcol[j] = rank of link j's source column in tcols.  The block's row pointers and
 // its links (a contiguous piece of the CSR; up to kCompactLinks of them) are staged in shared
 // memory first, so that a row costs one round trip to memory (its XT runs) instead of three.
+// The pass is bound by instruction issue, so the link loop is
+// kept lean: raw values first (RAW) -- the sums of a row whose sources are all finite are exactly
+// the filled sums -- and the 1e20 fill (regrid.py:545-547) only in a redo of the rows whose raw
+// sum came out non-finite; no batch-range predicates when the chunk is full (FULL); the links
+// read with plain shared-memory loads when they are staged (STAGED).
 constexpr int kCompactLinks = 1024;
 
+// the row again, with non-finite values replaced by 1e20 (out of line: keeps the common loop small).
+// Four links at a time, their loads unconditional and ahead of any use: with predicated loads the
+// compiler puts each value's non-finite test right behind its load and the links go one round trip
+// to memory at a time.  (XT rows are kCompactBC wide whatever bc is, slots behind the last link
+// re-read it; what lanes >= bc compute is never stored.)
+template <typename TX>
+__device__ __noinline__ double2 compact_row_filled(const TX *__restrict__ xt, const int32_t *rc, const double *vl,
+                                                   int j0, int j1, int lane)
+{
+    double a0 = 0.0, a1 = 0.0;
+    for (int j = j0; j < j1; j += 4) {
+        TX v0[4], v1[4];
+        double w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jj = j + u < j1 ? j + u : j1 - 1;
+            const TX *src = xt + static_cast<int64_t>(rc[jj]) * kCompactBC + lane;
+            w[u] = vl[jj];
+            v0[u] = __ldg(src);
+            v1[u] = kCompactBC > 32 ? __ldg(src + 32) : TX(0);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (j + u < j1) {
+                a0 = __dadd_rn(a0, __dmul_rn(static_cast<double>(fill_invalid(v0[u])), w[u]));
+                a1 = __dadd_rn(a1, __dmul_rn(static_cast<double>(fill_invalid(v1[u])), w[u]));
+            }
+        }
+    }
+    return make_double2(a0, a1);
+}
+
+template <typename TX, typename TY, bool FULL, bool STAGED, bool RAW>
+__device__ __forceinline__ void compact_rows(const TX *__restrict__ xt, int bc, const int32_t *rp, const int32_t *rc,
+                                             const double *vl, const uint8_t *dead_s, int nrows, int warp, int lane,
+                                             TY (*out)[kCompactRows + 1])
+{
+    for (int rl = warp; rl < nrows; rl += kCompactThreads / 32) {
+        double a0 = 0.0, a1 = 0.0;
+        const int j0 = rp[rl], j1 = rp[rl + 1];
+#pragma unroll 4
+        for (int j = j0; j < j1; ++j) {
+            const TX *src = xt + static_cast<int64_t>(rc[j]) * kCompactBC + lane;
+            const double wj = vl[j];
+            TX v0, v1;
+            if (FULL) {
+                v0 = __ldg(src);
+                v1 = kCompactBC > 32 ? __ldg(src + 32) : TX(0);
+            } else {
+                v0 = lane < bc ? __ldg(src) : TX(0);
+                v1 = lane + 32 < bc ? __ldg(src + 32) : TX(0);
+            }
+            if (!RAW) { v0 = fill_invalid(v0); v1 = fill_invalid(v1); }
+            a0 = __dadd_rn(a0, __dmul_rn(static_cast<double>(v0), wj));      // reference order, no FMA
+            a1 = __dadd_rn(a1, __dmul_rn(static_cast<double>(v1), wj));
+        }
+        // (a warp that remembers "the last row needed the fill" and skips the raw pass was measured:
+        // it costs the clean case more than it saves the other)
+        if (RAW && __any_sync(0xffffffffu, not_finite(a0) || not_finite(a1))) {
+            const double2 f = compact_row_filled<TX>(xt, rc, vl, j0, j1, lane);
+            a0 = f.x;
+            a1 = f.y;
+        }
+        if (a0 > 1e19) a0 = CUDART_NAN;                                       // regrid.py:570
+        if (a1 > 1e19) a1 = CUDART_NAN;
+        const bool dead = dead_s[rl] != 0;
+        out[lane][rl] = static_cast<TY>(dead ? CUDART_NAN : a0);
+        if (kCompactBC > 32) out[(lane + 32) % kCompactBC][rl] = static_cast<TY>(dead ? CUDART_NAN : a1);
+    }
+}
+
 template <typename TX, typename TY>
-__global__ void __launch_bounds__(kCompactThreads)
+__global__ void __launch_bounds__(kCompactThreads, 6)       // 6 blocks per SM: the out-of-line filled row must not raise the register count
 compact_apply_kernel(const TX *__restrict__ xt, int bc, const int32_t *__restrict__ rowptr,
                      const int32_t *__restrict__ rcol, const double *__restrict__ val,
                      const int32_t *__restrict__ imask, const double *__restrict__ frac, int masked,
-                     double remap_area_min, int64_t n_dst, TY *__restrict__ y, int64_t y_bstride)
+                     double remap_area_min, int64_t n_dst, TY *__restrict__ y, int64_t y_bstride, int raw_first)
 {
     __shared__ TY out[kCompactBC][kCompactRows + 1];
     __shared__ double val_s[kCompactLinks];
@@ -1144,27 +1220,17 @@ compact_apply_kernel(const TX *__restrict__ xt, int bc, const int32_t *__restric
         }
         __syncthreads();
     }
-    // generic pointers: shared memory when staged, else the CSR arrays themselves
-    const int32_t *rc = staged ? rcol_s - jb0 : rcol;
-    const double *vl = staged ? val_s - jb0 : val;
-    for (int rl = warp; rl < nrows; rl += kCompactThreads / 32) {
-        double a0 = 0.0, a1 = 0.0;
-        const int j1 = rp[rl + 1];
-#pragma unroll 4
-        for (int j = rp[rl]; j < j1; ++j) {
-            const TX *src = xt + static_cast<int64_t>(rc[j]) * kCompactBC;
-            const double wj = vl[j];
-            const TX v0 = lane < bc ? fill_invalid(__ldg(src + lane)) : TX(0);
-            const TX v1 = lane + 32 < bc ? fill_invalid(__ldg(src + lane + 32)) : TX(0);
-            a0 = __dadd_rn(a0, __dmul_rn(static_cast<double>(v0), wj));      // reference order, no FMA
-            a1 = __dadd_rn(a1, __dmul_rn(static_cast<double>(v1), wj));
-        }
-        if (a0 > 1e19) a0 = CUDART_NAN;                                       // regrid.py:570
-        if (a1 > 1e19) a1 = CUDART_NAN;
-        const bool dead = dead_s[rl] != 0;
-        out[lane][rl] = static_cast<TY>(dead ? CUDART_NAN : a0);
-        if (kCompactBC > 32) out[(lane + 32) % kCompactBC][rl] = static_cast<TY>(dead ? CUDART_NAN : a1);
-    }
+    const bool full = bc == kCompactBC;
+    // raw_first (rows of two or more links on average): sum raw values and redo the rows that came
+    // out non-finite; with one link per row the per-row work dominates and the fill stays in line
+    if (staged && full && raw_first)
+        compact_rows<TX, TY, true, true, true>(xt, bc, rp, rcol_s - jb0, val_s - jb0, dead_s, nrows, warp, lane, out);
+    else if (staged && full)
+        compact_rows<TX, TY, true, true, false>(xt, bc, rp, rcol_s - jb0, val_s - jb0, dead_s, nrows, warp, lane, out);
+    else if (staged)
+        compact_rows<TX, TY, false, true, false>(xt, bc, rp, rcol_s - jb0, val_s - jb0, dead_s, nrows, warp, lane, out);
+    else
+        compact_rows<TX, TY, false, false, false>(xt, bc, rp, rcol, val, dead_s, nrows, warp, lane, out);
     __syncthreads();
     for (int b = warp; b < bc; b += kCompactThreads / 32)
         if (lane < nrows) y[b * y_bstride + row0 + lane] = out[b][lane];

@@ -107,7 +107,7 @@ int launch_compact_t(int dev, const LevelDev &L, const JobSpec &sp, void *xt_raw
             static_cast<const TX *>(sp.x) + b0 * xbs, xbs, L.n_src, bc, L.tcols, L.blk_ptr, xt, bulk);
         compact_apply_kernel<TX, TY><<<grid2, kCompactThreads, 0, st>>>(
             xt, bc, L.rowptr, L.rcol, L.val, L.imask, L.frac, sp.masked, area_min, L.n_dst,
-            static_cast<TY *>(sp.y) + b0 * ybs, ybs);
+            static_cast<TY *>(sp.y) + b0 * ybs, ybs, L.nnz >= 2 * L.n_dst ? 1 : 0);
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return smm_fail(3, std::string("compact apply: ") + cudaGetErrorString(e));
         smm_count_launches(2);
