@@ -527,6 +527,12 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
                     if (dead) flags |= 16u << u;
                 }
             }
+            uint32_t dm[4];             // 0x7ff80000 for the sub-rows of dead rows, else 0
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                dm[u] = (flags & (16u << u)) ? 0x7ff80000u : 0u;
+                asm volatile("" : "+r"(dm[u]));          // opaque: kept in a register, not re-derived from `flags` per batch row
+            }
             TY *yb = static_cast<TY *>(job.y) + b0 * a.y_bstride;
             const TX *xp = static_cast<const TX *>(job.x) + b0 * a.x_bstride;
             const bool stream_only = (a.debug_flags & 1u) != 0;
@@ -589,8 +595,11 @@ staged_kernel(const __grid_constant__ JobBatch jb, const __grid_constant__ Apply
                     } else {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
+                            // a dead row's value becomes NaN by OR-ing exponent + quiet bit into its high
+                            // word: one LOP3 per store where the select on `flags` costs a test and two selects
                             if (rs[u] >= 0)
-                                store_y(yb + rs[u], static_cast<TY>((flags & (16u << u)) ? CUDART_NAN : acc[u]));
+                                store_y(yb + rs[u], static_cast<TY>(__hiloint2double(__double2hiint(acc[u]) | static_cast<int>(dm[u]),
+                                                                                     __double2loint(acc[u]))));
                         }
                     }
                 }
