@@ -107,6 +107,87 @@ def _is_dask(array) -> bool:
     return type(array).__module__.split(".")[0] == "dask"
 
 
+_PREFAULT_MIN_BYTES = 16 << 20
+_MADV_POPULATE_WRITE = 23          # Linux >= 5.14: make the pages present and writable, contents untouched
+
+
+def _prefault(addr: int, nbytes: int):
+    try:
+        libc = ctypes.CDLL(None)   # the process's own symbols: madvise of the C library
+        page = 4096
+        lo = (addr + page - 1) // page * page
+        hi = (addr + nbytes) // page * page
+        if hi > lo:
+            libc.madvise(ctypes.c_void_p(lo), ctypes.c_size_t(hi - lo), ctypes.c_int(_MADV_POPULATE_WRITE))
+    except Exception:              # an older kernel or another libc: the pages are faulted in by the copies instead
+        pass
+
+
+class _PinnedResults:
+    """Small pool of page-locked result buffers.  A result in pinned memory is written by the
+    device-to-host copies directly; a pageable one goes through the library's bounce buffers and
+    a host memcpy that, with 4-8 ranks sharing the host's memory system, costs 8 ms of a 74 ms
+    step (C4, 128 steps).  Allocating pinned memory per call is worse (3.6 ms for 66 MB), so
+    buffers are kept and handed out again once the caller has dropped the previous result: a
+    buffer is free when its storage has no user but the pool (views, and numpy arrays made from
+    them, count as users).  Capped; beyond the cap -- or without the storage-use-count hook of
+    this torch version -- results are ordinary pageable arrays."""
+
+    cap_bytes = 1 << 30
+    min_bytes = 8 << 20
+
+    def __init__(self):
+        import threading
+        self._bufs = []            # (flat uint8 pinned tensor, its storage use count when idle)
+        self._lock = threading.Lock()
+
+    @staticmethod
+    def _alloc(nbytes):
+        return _torch().empty(nbytes, dtype=_torch().uint8, pin_memory=True)
+
+    @staticmethod
+    def _users(t) -> int:
+        return _torch()._C._storage_Use_Count(t.untyped_storage()._cdata)
+
+    def take(self, shape, dtype):
+        """pinned torch tensor of that shape / numpy dtype, or None (small result, cap reached, no hook)"""
+        torch = _torch()
+        nbytes = int(np.prod(shape, dtype=np.int64)) * np.dtype(dtype).itemsize
+        if nbytes < self.min_bytes or nbytes > self.cap_bytes or not hasattr(torch._C, "_storage_Use_Count"):
+            return None
+        with self._lock:
+            # (idle count measured per buffer when it is created: the tensor itself, the temporary
+            # storage handle and whatever the allocator of this torch build keeps)
+            base = next((t for t, idle in self._bufs if nbytes <= t.numel() <= 2 * nbytes and self._users(t) <= idle), None)
+            if base is None:
+                if sum(t.numel() for t, _ in self._bufs) + nbytes > self.cap_bytes:
+                    return None
+                try:
+                    base = self._alloc(nbytes)
+                except RuntimeError:
+                    return None
+                self._bufs.append((base, self._users(base)))
+            tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+            return base[:nbytes].view(tdt).reshape(tuple(int(n) for n in shape))
+
+
+_pinned_results = _PinnedResults()
+
+
+def _new_host_result(shape, dtype) -> np.ndarray:
+    """Pageable result array.  Its pages are new to the process: the first write to each makes the
+    kernel map and zero-fill it (~7 ms for the 66 MB of a 128-step C4 result when the ranks of an
+    8-GPU box all do that at once), and those first writes would be the library's result copies,
+    in line with the device pipeline.  A helper thread asks the kernel to populate the pages
+    (``madvise(MADV_POPULATE_WRITE)``: contents untouched, so it is safe next to the copies) while
+    the first chunks are still on their way to the device."""
+    a = np.empty(shape, dtype=dtype)
+    if a.nbytes >= _PREFAULT_MIN_BYTES:
+        import threading
+        threading.Thread(target=_prefault, args=(a.ctypes.data, a.nbytes), daemon=True).start()
+    return a
+
+
 def remove_degenerate_axes(values, dims):
     """``smmregrid/dimension.py:22-37`` on a bare array: every axis along which all values
     are identical is averaged away.  Returns ``(values, dims)``."""
@@ -327,7 +408,9 @@ class Regridder(object):
                 raise ValueError("out= needs transpose=True and a C-contiguous array")
             y = torch.from_numpy(out.reshape(T, Ld, self.n_dst))
         else:
-            y = torch.from_numpy(np.empty((T, Ld, self.n_dst), dtype=self._out_np_dtype()))
+            y = _pinned_results.take((T, Ld, self.n_dst), self._out_np_dtype())
+            if y is None:
+                y = torch.from_numpy(_new_host_result((T, Ld, self.n_dst), self._out_np_dtype()))
         _lib.check(_lib.load().smm_apply_levels_host(
             self.weights_matrix.handle, Ld, widx.ctypes.data_as(ctypes.c_void_p),
             ctypes.c_void_p(x.data_ptr()), _np_dtype_code(_np_of(x.dtype)), T,
@@ -370,10 +453,12 @@ class Regridder(object):
                     raise ValueError("out= must be a C-contiguous array")
                 y = torch.from_numpy(out.reshape(B, self.n_dst))
             else:
-                # pageable, untouched memory: the library returns the (50-100x smaller) result through
-                # its own pinned bounce buffers, overlapped with the transfers still in flight -- a
-                # pinned allocation per call would cost more than that (3.6 ms for 66 MB, measured)
-                y = torch.from_numpy(np.empty((B, self.n_dst), dtype=self._out_np_dtype()))
+                # a recycled pinned buffer (the device-to-host copies write it directly), else
+                # pageable memory: the library then returns the result through its own pinned bounce
+                # buffers -- a pinned allocation per call costs more than that (3.6 ms for 66 MB)
+                y = _pinned_results.take((B, self.n_dst), self._out_np_dtype())
+                if y is None:
+                    y = torch.from_numpy(_new_host_result((B, self.n_dst), self._out_np_dtype()))
             _lib.check(lib.smm_apply_host(
                 parent.handle, lvl, ctypes.c_void_p(xt.data_ptr()), _np_dtype_code(_np_of(xt.dtype)), B,
                 self.n_src, ctypes.c_void_p(y.data_ptr()), _np_dtype_code(_np_of(y.dtype)), self.n_dst,
@@ -532,7 +617,7 @@ class Regridder(object):
         """Host-backed (numpy or lazily indexed) data: blocks of the leading kept dim are read,
         pushed through the device pipeline and written straight into the result, so no more than
         ``host_block_bytes`` of the source is ever held (``regrid.py:538-550`` keeps the field lazy)."""
-        out = np.empty(kept_shape + self.tgt_shape, dtype=out_dt)
+        out = _new_host_result(kept_shape + self.tgt_shape, out_dt)
         if not other or da.shape[0] <= 1:
             self._block_apply(da.values, levels, out=out)
             return out
