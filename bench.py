@@ -474,8 +474,8 @@ def main():
         yw = None
         for _ in range(3):                                        # and the pool of pinned result buffers: a loop that
             yw = rg.regrid(xh)                                    # keeps its last result, like the timed one, needs two
-        te = timed_regrids(xh, args.e2e_steps)
         del yw
+        te = timed_regrids(xh, args.e2e_steps)
         e2e_val = world * Be * n_src * args.e2e_steps / te
         # what the PCIe links themselves sustain: bare cudaMemcpyAsync of the same pinned bytes,
         # all ranks at the same time (and the result's bytes in the other direction)

@@ -130,15 +130,20 @@ class _PinnedResults:
     step (C4, 128 steps).  Allocating pinned memory per call is worse (3.6 ms for 66 MB), so
     buffers are kept and handed out again once the caller has dropped the previous result: a
     buffer is free when its storage has no user but the pool (views, and numpy arrays made from
-    them, count as users).  Capped; beyond the cap -- or without the storage-use-count hook of
-    this torch version -- results are ordinary pageable arrays."""
+    them, count as users).  Page-locking is expensive in a process that already holds tens of GB
+    (~100 ms for 66 MB next to the bench's 28 GB slab), so the pool only serves a result size it
+    has been asked for before (a loop), keeps at most two buffers per size -- what
+    ``y = rg.regrid(x)`` in a loop needs -- and is capped; everything else, and every torch
+    build without the storage-use-count hook, gets ordinary pageable arrays."""
 
     cap_bytes = 1 << 30
     min_bytes = 8 << 20
+    per_size = 2
 
     def __init__(self):
         import threading
         self._bufs = []            # (flat uint8 pinned tensor, its storage use count when idle)
+        self._asked = {}           # result size -> times requested
         self._lock = threading.Lock()
 
     @staticmethod
@@ -158,9 +163,12 @@ class _PinnedResults:
         with self._lock:
             # (idle count measured per buffer when it is created: the tensor itself, the temporary
             # storage handle and whatever the allocator of this torch build keeps)
-            base = next((t for t, idle in self._bufs if nbytes <= t.numel() <= 2 * nbytes and self._users(t) <= idle), None)
+            self._asked[nbytes] = self._asked.get(nbytes, 0) + 1
+            fits = [(t, idle) for t, idle in self._bufs if nbytes <= t.numel() <= 2 * nbytes]
+            base = next((t for t, idle in fits if self._users(t) <= idle), None)
             if base is None:
-                if sum(t.numel() for t, _ in self._bufs) + nbytes > self.cap_bytes:
+                if self._asked[nbytes] < 2 or len(fits) >= self.per_size or \
+                        sum(t.numel() for t, _ in self._bufs) + nbytes > self.cap_bytes:
                     return None
                 try:
                     base = self._alloc(nbytes)

@@ -4,17 +4,19 @@ import torch
 
 
 def test_pinned_result_pool_recycles_only_dropped_results(monkeypatch):
-    """Results are handed out in recycled page-locked buffers (here: ordinary memory, no GPU): a
-    buffer is reused only after every view / numpy array of the previous result is gone, a result
-    still held gets a different buffer, the cap and the size window are respected."""
+    """Results are handed out in recycled page-locked buffers (here: ordinary memory, no GPU): only
+    for a size that was asked for before (a loop), a buffer is reused only after every view /
+    numpy array of the previous result is gone, a result still held gets the second buffer of its
+    size, a third concurrent result falls back to pageable memory (None)."""
     import sys
     import smmregrid_b200  # noqa: F401
     mod = sys.modules["smmregrid_b200.regrid"]
     pool = mod._PinnedResults()
     monkeypatch.setattr(pool, "_alloc", lambda nbytes: torch.empty(nbytes, dtype=torch.uint8))
-    pool.min_bytes, pool.cap_bytes = 1024, 3 * 4096 * 8
-    assert pool.take((4, 4), np.float64) is None                       # too small
+    pool.min_bytes = 1024
     assert pool._users(torch.empty(8, dtype=torch.uint8)) >= 1
+    assert pool.take((4, 4), np.float64) is None                       # too small
+    assert pool.take((4, 1024), np.float64) is None                    # first request of this size: not a loop yet
     a = pool.take((4, 1024), np.float64)
     assert a.shape == (4, 1024) and a.dtype == torch.float64 and len(pool._bufs) == 1
     ptr_a = a.data_ptr()
@@ -24,15 +26,17 @@ def test_pinned_result_pool_recycles_only_dropped_results(monkeypatch):
     assert b.data_ptr() != ptr_a and len(pool._bufs) == 2
     view = an.reshape(-1)[10:]
     del an
-    c = pool.take((4, 1024), np.float32)                                # a derived numpy view still holds it; f32 is half the size: fits
-    assert c.data_ptr() not in (ptr_a,) and len(pool._bufs) == 3
+    assert pool.take((4, 1024), np.float64) is None                     # a derived numpy view still holds the first, b the second
     del view
     d = pool.take((4, 1024), np.float64)                                # first buffer is free again
-    assert d.data_ptr() == ptr_a and len(pool._bufs) == 3
-    assert pool.take((4, 1024), np.float64) is None                     # all in use, cap reached -> pageable fallback
-    del b, c, d
+    assert d.data_ptr() == ptr_a and len(pool._bufs) == 2
+    del b, d
+    pool.take((3, 1024), np.float64)
     e = pool.take((3, 1024), np.float64)                                # a slightly smaller result reuses a buffer
-    assert e.data_ptr() == ptr_a and e.shape == (3, 1024)
+    assert e.data_ptr() == ptr_a and e.shape == (3, 1024) and len(pool._bufs) == 2
+    pool.cap_bytes = 4 * 1024 * 8 * 2                                   # the cap stops a new size class
+    pool.take((64, 1024), np.float64)
+    assert pool.take((64, 1024), np.float64) is None
 
 
 def test_new_host_result_prefault_keeps_contents():
